@@ -1,0 +1,326 @@
+"""CPU ORACLE (Python side) -- TEST INFRASTRUCTURE ONLY, NOT A PRODUCT PATH.
+
+ctypes bindings for oracle/delight_oracle.c plus NumPy restatements of the Python-level algebra
+on Delight's hot path (GP fit / predict, metrics, template-fitting likelihood).  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline leg may import this module; nothing under
+delight_b200/ does.
+
+Parity status: PINNED against the compiled reference (oracle/_ref) through the fixtures in
+tests/golden/ (see tests/test_oracle.py) and the reference's own golden vectors.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_lp = ctypes.POINTER(ctypes.c_long)
+
+
+def build():
+    so = os.path.join(HERE, "liboracle.so")
+    src = os.path.join(HERE, "delight_oracle.c")
+    if (not os.path.exists(so)) or os.path.getmtime(so) < os.path.getmtime(src):
+        cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+        subprocess.check_call([cc, "-O2", "-fPIC", "-fopenmp", "-shared", "-o", so, src, "-lm"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(build())
+        _LIB.orc_num_threads.restype = ctypes.c_int
+    return _LIB
+
+
+def _d(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(_dp)
+
+
+def _l(a):
+    a = np.ascontiguousarray(a, dtype=np.int64)
+    return a, a.ctypes.data_as(_lp)
+
+
+# ------------------------------------------------------------------------------------------------
+# likelihood  (delight/utils_cy.pyx:83-128)
+# ------------------------------------------------------------------------------------------------
+def flux_loglike(f_obs, f_obs_var, f_mod, f_mod_covar, ell_hat, ell_var):
+    nz, nt, nf = f_mod.shape
+    out = np.zeros((nz, nt))
+    keep = [_d(f_obs), _d(f_obs_var), _d(f_mod), _d(f_mod_covar), _d(ell_hat), _d(ell_var)]
+    lib().orc_flux_loglike(out.ctypes.data_as(_dp), ctypes.c_long(nz), ctypes.c_long(nt),
+                           ctypes.c_long(nf), *[k[1] for k in keep])
+    return out
+
+
+def approx_flux_likelihood_cy(like, nz, nt, nf, f_obs, f_obs_var, f_mod, f_mod_covar,
+                              ell_hat, ell_var):
+    """Same signature and in-place contract as delight/utils_cy.pyx:83-94."""
+    out = np.zeros((nz, nt))
+    keep = [_d(f_obs), _d(f_obs_var), _d(f_mod), _d(f_mod_covar), _d(ell_hat), _d(ell_var)]
+    lib().orc_approx_flux_likelihood(out.ctypes.data_as(_dp), ctypes.c_long(nz),
+                                     ctypes.c_long(nt), ctypes.c_long(nf),
+                                     *[k[1] for k in keep])
+    like[...] = out
+
+
+def apply_fused(fluxes, fluxes_var, nf, bands, model_mean, model_covar, prior, zgrid,
+                ell_hat, ell_var, K, want_evid=False):
+    """Batch of targets through likelihood + the apply epilogue (delight-apply.py:137-162).
+
+    fluxes, fluxes_var, bands: [nO, nB] packed left (first nf[o] entries valid).
+    model_mean/model_covar: [nz, nT, nB];  prior: [nz, nT].
+    Returns dict(pdf [nO,nz], top_idx [nO,K], top_ev [nO,K], like_max_pos [nO], evid [nO,nT]|None).
+    """
+    nz, nT, nB = model_mean.shape
+    nO = fluxes.shape[0]
+    pdf = np.zeros((nO, nz))
+    top_idx = np.zeros((nO, max(K, 1)), dtype=np.int64)
+    top_ev = np.zeros((nO, max(K, 1)))
+    pos = np.zeros(nO, dtype=np.int64)
+    evid = np.zeros((nO, nT)) if want_evid else None
+    keep = [_l(nf), _l(bands), _d(fluxes), _d(fluxes_var), _d(model_mean), _d(model_covar),
+            _d(prior), _d(zgrid), _d(ell_hat), _d(ell_var)]
+    lib().orc_apply_fused(ctypes.c_long(nO), ctypes.c_long(nT), ctypes.c_long(nz),
+                          ctypes.c_long(nB), ctypes.c_long(K), *[k[1] for k in keep],
+                          pdf.ctypes.data_as(_dp),
+                          evid.ctypes.data_as(_dp) if want_evid else None,
+                          top_idx.ctypes.data_as(_lp), top_ev.ctypes.data_as(_dp),
+                          pos.ctypes.data_as(_lp))
+    return dict(pdf=pdf, top_idx=top_idx[:, :K], top_ev=top_ev[:, :K], like_max_pos=pos,
+                evid=evid)
+
+
+# ------------------------------------------------------------------------------------------------
+# GP kernel pieces  (delight/photoz_kernels_cy.pyx)
+# ------------------------------------------------------------------------------------------------
+def kernelparts(NO1, NO2, NC, NL, alpha_C, alpha_L, fcoefs_amp, fcoefs_mu, fcoefs_sig,
+                lines_mu, lines_sig, norms, b1, fz1, b2, fz2, grad_needed,
+                KL, KC, D_alpha_C, D_alpha_L, D_alpha_z):
+    """Same signature / accumulate-then-normalise contract as photoz_kernels_cy.pyx:103-122."""
+    outs = [np.ascontiguousarray(a, dtype=np.float64).copy()
+            for a in (KL, KC, D_alpha_C, D_alpha_L, D_alpha_z)]
+    keep = [_d(fcoefs_amp), _d(fcoefs_mu), _d(fcoefs_sig), _d(lines_mu), _d(norms)]
+    kb1, kf1, kb2, kf2 = _l(b1), _d(fz1), _l(b2), _d(fz2)
+    lib().orc_kernelparts(int(NO1), int(NO2), int(NC), int(NL), ctypes.c_double(alpha_C),
+                          ctypes.c_double(alpha_L), *[k[1] for k in keep],
+                          kb1[1], kf1[1], kb2[1], kf2[1], int(bool(grad_needed)),
+                          *[o.ctypes.data_as(_dp) for o in outs])
+    for dst, src in zip((KL, KC, D_alpha_C, D_alpha_L, D_alpha_z), outs):
+        dst[...] = src
+
+
+def kernelparts_diag(NO1, NC, NL, alpha_C, alpha_L, fcoefs_amp, fcoefs_mu, fcoefs_sig,
+                     lines_mu, lines_sig, norms, b1, fz1, grad_needed,
+                     KL, KC, D_alpha_C, D_alpha_L):
+    """photoz_kernels_cy.pyx:38-54."""
+    outs = [np.ascontiguousarray(a, dtype=np.float64).copy()
+            for a in (KL, KC, D_alpha_C, D_alpha_L)]
+    keep = [_d(fcoefs_amp), _d(fcoefs_mu), _d(fcoefs_sig), _d(lines_mu), _d(norms)]
+    kb1, kf1 = _l(b1), _d(fz1)
+    lib().orc_kernelparts_diag(int(NO1), int(NC), int(NL), ctypes.c_double(alpha_C),
+                               ctypes.c_double(alpha_L), *[k[1] for k in keep],
+                               kb1[1], kf1[1], int(bool(grad_needed)),
+                               *[o.ctypes.data_as(_dp) for o in outs])
+    for dst, src in zip((KL, KC, D_alpha_C, D_alpha_L), outs):
+        dst[...] = src
+
+
+def find_positions(NO1, nz, fz1, p1s, fzGrid):
+    """utils_cy.pyx:10-22 (entries outside the grid are left untouched)."""
+    p = np.ascontiguousarray(p1s, dtype=np.int64).copy()
+    kf, kg = _d(fz1), _d(fzGrid)
+    lib().orc_find_positions(int(NO1), int(nz), kf[1], p.ctypes.data_as(_lp), kg[1])
+    p1s[...] = p
+
+
+def kernel_parts_interp(NO1, NO2, Kinterp, b1, fz1, p1s, b2, fz2, p2s, fzGrid, Kgrid):
+    """photoz_kernels_cy.pyx:9-35."""
+    out = np.zeros((NO1, NO2))
+    nB, _, nzg, _ = Kgrid.shape
+    keep = [_l(b1), _d(fz1), _l(p1s), _l(b2), _d(fz2), _l(p2s), _d(fzGrid), _d(Kgrid)]
+    lib().orc_kernel_parts_interp(int(NO1), int(NO2), out.ctypes.data_as(_dp),
+                                  *[k[1] for k in keep], ctypes.c_long(nB), ctypes.c_long(nzg))
+    Kinterp[...] = out
+
+
+# ------------------------------------------------------------------------------------------------
+# NumPy restatements of the Python-level algebra
+# ------------------------------------------------------------------------------------------------
+def approx_DL(z):
+    """delight/utils.py:12-13."""
+    return np.exp(30.5 * np.asarray(z, dtype=float) ** 0.04 - 21.7)
+
+
+def zeta(z, g_AB=1.0):
+    """sqrt of the kernel prefactor: Zprefac(z,z') = zeta(z) zeta(z')  (photoz_kernels.py:338-340)."""
+    z = np.asarray(z, dtype=float)
+    return (1.0 + z) / (np.sqrt(4 * np.pi * g_AB) * approx_DL(z))
+
+
+def kernel_grids(amp, mu, sig, lines_mu, alpha_C, alpha_L, redshiftGridGP):
+    """Photoz_kernel.construct_interpolators (photoz_kernels.py:342-416): KC/KL on the
+    (nB,nB,nzGP,nzGP) grid and the per-band diagonals (nB,nzGP)."""
+    nB, NC = amp.shape
+    NL = len(lines_mu)
+    nzg = len(redshiftGridGP)
+    norms = np.sqrt(2 * np.pi) * np.sum(amp * sig, axis=1)
+    fz = 1.0 + np.asarray(redshiftGridGP, dtype=float)
+    KC = np.zeros((nB, nB, nzg, nzg))
+    KL = np.zeros_like(KC)
+    scratch = [np.zeros((nzg, nzg)) for _ in range(3)]
+    for i in range(nB):
+        for j in range(nB):
+            kc = np.zeros((nzg, nzg))
+            kl = np.zeros((nzg, nzg))
+            for s in scratch:
+                s[...] = 0
+            kernelparts(nzg, nzg, NC, NL, alpha_C, alpha_L, amp, mu, sig, lines_mu, None, norms,
+                        np.full(nzg, i), fz, np.full(nzg, j), fz, True, kl, kc, *scratch)
+            KC[i, j], KL[i, j] = kc, kl
+    KCd = np.zeros((nB, nzg))
+    KLd = np.zeros((nB, nzg))
+    for i in range(nB):
+        d = [np.zeros(nzg) for _ in range(4)]
+        kernelparts_diag(nzg, NC, NL, alpha_C, alpha_L, amp, mu, sig, lines_mu, None, norms,
+                         np.full(nzg, i), fz, True, *d)
+        KLd[i], KCd[i] = d[0], d[1]
+    return dict(KC=KC, KL=KL, KCd=KCd, KLd=KLd, norms=norms, fzGrid=fz)
+
+
+def _bilinear(G, fzGrid, b1, x1, b2, x2):
+    p1 = np.zeros(len(x1), dtype=np.int64)
+    p2 = np.zeros(len(x2), dtype=np.int64)
+    find_positions(len(x1), len(fzGrid), x1, p1, fzGrid)
+    find_positions(len(x2), len(fzGrid), x2, p2, fzGrid)
+    out = np.zeros((len(x1), len(x2)))
+    kernel_parts_interp(len(x1), len(x2), out, b1, x1, p1, b2, x2, p2, fzGrid, G)
+    return out
+
+
+def interp_lin_extrap(xg, yg, x):
+    """scipy interp1d(kind='linear', fill_value='extrapolate') on a sorted grid."""
+    xg = np.asarray(xg, dtype=float)
+    yg = np.asarray(yg, dtype=float)
+    x = np.atleast_1d(np.asarray(x, dtype=float))
+    i = np.clip(np.searchsorted(xg, x, side="left") - 1, 0, len(xg) - 2)
+    # scipy: searchsorted(x_new) then clip to [1, len-1]; lo = that - 1
+    i = np.clip(np.searchsorted(xg, x), 1, len(xg) - 1) - 1
+    slope = (yg[i + 1] - yg[i]) / (xg[i + 1] - xg[i])
+    return slope * (x - xg[i]) + yg[i]
+
+
+def scalefree_best_type(fluxes, fluxes_var, tmpl):
+    """delight-learn.py:67-79 with utils.py:179-193: tmpl [nt, B] = template fluxes at the
+    galaxy's z in its valid bands.  Returns (bestType, ell)."""
+    w = np.where(fluxes / fluxes_var < 1e-6, 0.0, 1.0 / fluxes_var)
+    FOT = np.sum(tmpl * fluxes * w, axis=1)
+    FTT = np.sum(tmpl ** 2 * w, axis=1)
+    FOO = np.dot(w, fluxes ** 2)
+    chi2 = FOO - FOT ** 2 / FTT
+    best = int(np.argmin(chi2 + FTT))            # utils.py:191 returns chi2 + FTT
+    return best, (FOT / FTT)[best]
+
+
+def gp_fit(grids, V_C, V_L, tmpl_table, zfine, bands, z, fluxes, fluxes_var):
+    """Per-training-galaxy fit (photoz_gp.py:186-234, delight-learn.py:61-90).
+
+    tmpl_table [nt, nB, nzfine]: template fluxes on the fine grid `zfine`
+    (<sed>_fluxredshiftmod.txt); evaluated at z by linear interpolation with extrapolation.
+    Returns dict(bestType, ell, L [B,B], D [B], beta [B], core flat array).
+    """
+    import scipy.linalg
+    bands = np.asarray(bands, dtype=np.int64)
+    B = len(bands)
+    nt = tmpl_table.shape[0]
+    tm = np.array([[interp_lin_extrap(zfine, tmpl_table[t, b], z)[0] for b in bands]
+                   for t in range(nt)])
+    best, ell = scalefree_best_type(fluxes, fluxes_var, tm)
+    x = np.full(B, 1.0 + z)
+    kc = _bilinear(grids["KC"], grids["fzGrid"], bands, x, bands, x)
+    kl = _bilinear(grids["KL"], grids["fzGrid"], bands, x, bands, x)
+    pref = zeta(z) ** 4 * ell * ell
+    A = pref * (V_C * kc + V_L * kl) + np.diag(fluxes_var)
+    L = scipy.linalg.cholesky(A, lower=True)
+    hx = ell * tm[best]
+    hx = np.where(np.isfinite(hx), hx, 0.0)
+    D = fluxes - hx
+    beta = scipy.linalg.cho_solve((L, True), D)
+    core = np.zeros(nt + B * (B + 1) // 2 + B)
+    core[best] = 1.0
+    core[nt:nt + B * (B + 1) // 2] = L[np.tril_indices(B)]
+    core[nt + B * (B + 1) // 2:] = D
+    return dict(bestType=best, ell=ell, L=L, D=D, beta=beta, core=core, A=A)
+
+
+def gp_predict_interp(grids, V_C, V_L, tmpl_table, zfine, redshiftGridGP, bands, z, ell,
+                      bestType, L, D, redshiftGrid):
+    """setCore + predictAndInterpolate (photoz_gp.py:236-347) -> model_mean, model_var [nz, nB]."""
+    import scipy.linalg
+    nB = grids["KC"].shape[0]
+    zg = np.asarray(redshiftGridGP, dtype=float)
+    nzg = len(zg)
+    bands = np.asarray(bands, dtype=np.int64)
+    B = len(bands)
+    beta = scipy.linalg.cho_solve((L, True), D)
+    bstar = np.repeat(np.arange(nB), nzg)
+    xstar = np.tile(1.0 + zg, nB)
+    x = np.full(B, 1.0 + z)
+    kc = _bilinear(grids["KC"], grids["fzGrid"], bstar, xstar, bands, x)
+    kl = _bilinear(grids["KL"], grids["fzGrid"], bstar, xstar, bands, x)
+    zs = np.tile(zg, nB)
+    k = (zeta(zs) ** 2)[:, None] * zeta(z) ** 2 * ell * ell * (V_C * kc + V_L * kl)
+    v = scipy.linalg.cho_solve((L, True), k.T)
+    kd = zeta(zs) ** 4 * ell * ell * (V_C * grids["KCd"].ravel() + V_L * grids["KLd"].ravel())
+    var = kd - np.einsum("ij,ji->i", k, v)
+    mf = ell * np.concatenate([interp_lin_extrap(zfine, tmpl_table[bestType, b], zg)
+                               for b in range(nB)])
+    mean = k @ beta + mf
+    model_mean = np.zeros((len(redshiftGrid), nB))
+    model_var = np.zeros_like(model_mean)
+    for b in range(nB):
+        model_mean[:, b] = interp_lin_extrap(zg, mean[b * nzg:(b + 1) * nzg], redshiftGrid)
+        model_var[:, b] = interp_lin_extrap(zg, var[b * nzg:(b + 1) * nzg], redshiftGrid)
+    return model_mean, model_var
+
+
+def z_prior(redshiftGrid, train_z, zPriorSigma):
+    """delight-apply.py:104."""
+    return np.exp(-0.5 * ((redshiftGrid[:, None] - train_z[None, :]) / zPriorSigma) ** 2)
+
+
+def template_prior(redshiftGrid, p_t, p_z_t):
+    """scripts/templateFitting.py:79-82."""
+    b2 = np.asarray(p_z_t, dtype=float) ** 2.0
+    zz = redshiftGrid[:, None]
+    return np.asarray(p_t)[None, :] * zz / b2[None, :] * np.exp(-0.5 * zz ** 2 / b2[None, :])
+
+
+def metrics_core(ztrue, redshiftGrid, pdf):
+    """First seven columns of computeMetrics (utils.py:213-227)."""
+    zmean = np.average(redshiftGrid, weights=pdf)
+    imap = int(np.argmax(pdf))
+    zmap = redshiftGrid[imap]
+    s1 = np.sqrt(np.average((redshiftGrid - zmean) ** 2, weights=pdf))
+    s2 = np.sqrt(np.average((redshiftGrid - zmap) ** 2, weights=pdf))
+    return np.array([ztrue, zmean, s1, zmap, s2, np.interp(ztrue, redshiftGrid, pdf),
+                     np.interp(ztrue, redshiftGrid, pdf.cumsum())]), imap
+
+
+def ci_level(redshiftGrid, pdf, fraction, numlevels=200):
+    """utils.py:196-205."""
+    def trapz(y, x):
+        return np.sum((x[1:] - x[:-1]) * (y[1:] + y[:-1]) * 0.5) if len(x) > 1 else 0.0
+    ev = trapz(pdf, redshiftGrid)
+    for level in np.linspace(0, pdf.max(), num=numlevels):
+        ind = np.where(pdf <= level)
+        if trapz(pdf[ind], redshiftGrid[ind]) >= fraction * ev:
+            return level
+    return None
