@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""Headline benchmark: galaxy-PDFs/s through the fused photo-z likelihood (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (config.workload): BASELINE.json configs[2] -- 10k targets x 10k training GPs x 1500
+redshifts x 6 bands (LSST ugrizy), fused PDF + top-50, float64 -- the largest configuration that
+is quoted per single B200; per GPU when N > 1 (weak scaling: every rank owns 10k targets, the
+model grid is replicated, no data-path collective; results are gathered to rank 0 over NCCL).
+A "step" is one pass of the hot path over the rank's target batch.
+
+One JSON line is printed by rank 0 (see the keys below).  `value` = targets/s with inputs
+resident in HBM; `e2e` = the same through the public API with host buffers (H2D of the target
+fluxes from pinned memory and D2H of PDFs / top-K inside the timed region).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+N_TARGETS = 10000
+N_TRAIN = 10000
+N_COMPRESS = 50
+ELL_VAR = 0.25            # ellPriorSigma 0.5 (tests/parametersTest.cfg:57)
+Z_PRIOR_SIGMA = 0.5
+FLOP_PER_CELL = lambda nf: 27 * nf + 30     # SURVEY.md 8(d), fused path
+
+
+def workload_name(nO, nT, nz, nB):
+    return ("C3 approx_flux_likelihood fused PDF+top-%d: %d targets x %d training GPs x %d z "
+            "x %d bands (LSST ugrizy), f64" % (N_COMPRESS, nO, nT, nz, nB))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation of the path, on the host cores
+# --------------------------------------------------------------------------------------------
+def reference_step(cy_like, model_mean, model_covar, prior, zgrid, cat, first, count):
+    """Loop body of scripts/delight-apply.py:114-162 for `count` targets (all bands valid)."""
+    nz, nT, nB = model_mean.shape
+    bands = np.arange(nB)
+    out = []
+    for o in range(first, first + count):
+        ell_hat_z = np.ones(nz)
+        like_grid = np.zeros((nz, nT))
+        cy_like(like_grid, nz, nT, bands.size, cat["fluxes"][o], cat["fluxes_var"][o],
+                model_mean[:, :, bands], model_covar[:, :, bands],
+                ell_hat=ell_hat_z, ell_var=(ell_hat_z * np.sqrt(ELL_VAR)) ** 2)
+        like_grid *= prior
+        pdf = like_grid.sum(axis=1)
+        evidences = np.trapz(like_grid, x=zgrid, axis=0)
+        sortind = np.argsort(evidences)[::-1][0:N_COMPRESS]
+        out.append((pdf, sortind, evidences[sortind]))
+    return out
+
+
+def host_model_grid(nT, data, nB):
+    """Same stand-in model grid as the GPU arm, built on the host."""
+    from delight_b200 import workloads
+    mean, var, zt = workloads.standin_model_grid(nT, data, seed=1, nB=nB, device="cpu")
+    return mean.numpy(), var.numpy(), zt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from delight_b200 import workloads
+    from oracle import ref, oracle as orc
+    data = workloads.load_lsst()
+    nz, nB = data["zgrid"].size, data["tmpl"].shape[1]
+    cores = os.cpu_count() or 1
+    if ref.available():
+        ref.load()
+        from delight.utils_cy import approx_flux_likelihood_cy as cy_like
+        kind = "reference"
+    else:
+        cy_like, kind = orc.approx_flux_likelihood_cy, "port"
+    nT = args.train
+    model_mean, model_covar, zt = host_model_grid(nT, data, nB)
+    zgrid = data["zgrid"]
+    prior = orc.z_prior(zgrid, zt, Z_PRIOR_SIGMA)
+    per_step = args.ref_targets
+    cat = workloads.mock_catalogue(per_step * (args.steps + args.warmup), data, seed=2)
+    for w in range(args.warmup):
+        reference_step(cy_like, model_mean, model_covar, prior, zgrid, cat, w * per_step, 1)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        reference_step(cy_like, model_mean, model_covar, prior, zgrid, cat,
+                       (args.warmup + s) * per_step, per_step)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "galaxy-PDFs/sec", "value": value, "unit": "galaxies/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(N_TARGETS, nT, nz, nB),
+                   "inputs": "larger than L2 (model grid 2 x %.0f MB)" % (model_mean.nbytes / 1e6)},
+        "cpu_baseline": {"value": value, "unit": "galaxies/s", "cores": cores, "kind": kind,
+                         "sample": "%d targets/step against the full %d x %d x %d grid, loop "
+                                   "body of delight-apply.py:114-162 incl. its per-target "
+                                   "fancy-index copies of the grid; OpenMP over %d threads"
+                                   % (per_step, nz, nT, nB, cores)},
+        "e2e": {"value": value, "unit": "galaxies/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------------
+def cpu_baseline_sample(data, nT, nB, budget_s=20.0):
+    """Reference loop body timed on the host cores of this box on a bounded sample."""
+    from delight_b200 import workloads
+    from oracle import ref, oracle as orc
+    if ref.available():
+        ref.load()
+        from delight.utils_cy import approx_flux_likelihood_cy as cy_like
+        kind = "reference"
+    else:
+        cy_like, kind = orc.approx_flux_likelihood_cy, "port"
+    model_mean, model_covar, zt = host_model_grid(nT, data, nB)
+    zgrid = data["zgrid"]
+    prior = orc.z_prior(zgrid, zt, Z_PRIOR_SIGMA)
+    cat = workloads.mock_catalogue(64, data, seed=2)
+    reference_step(cy_like, model_mean, model_covar, prior, zgrid, cat, 0, 1)     # warm
+    n, t0 = 0, time.perf_counter()
+    while n < 64 and (time.perf_counter() - t0 < budget_s or n < 3):
+        reference_step(cy_like, model_mean, model_covar, prior, zgrid, cat, n, 1)
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "galaxies/s", "cores": os.cpu_count() or 1, "kind": kind,
+            "sample": "%d targets against the full %d x %d x %d grid (loop body of "
+                      "delight-apply.py:114-162 incl. its per-target fancy-index grid copies), "
+                      "%.1f s" % (n, zgrid.size, nT, nB, dt)}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from delight_b200 import _lib, apply, workloads
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = _lib.lib()
+
+    data = workloads.load_lsst()
+    zgrid = data["zgrid"]
+    nz, nB = zgrid.size, data["tmpl"].shape[1]
+    nT, nO = args.train, args.targets
+    mean, var, zt = workloads.standin_model_grid(nT, data, seed=1)           # replicated
+    grid = apply.ModelGrid.from_legacy(mean, var)
+    del mean, var
+    prior = grid.gaussian_prior(zgrid, zt, Z_PRIOR_SIGMA)
+    cat = workloads.mock_catalogue(nO, data, seed=100 + rank)                # this rank's shard
+    targets = apply.Targets.full(cat["fluxes"], cat["fluxes_var"], cat["z"])
+    ws = apply.FusedWorkspace()
+    zg_dev = torch.from_numpy(zgrid).cuda()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(tg):
+        return apply.apply_fused(grid, prior, zg_dev, tg, ell_hat=1.0, ell_var=ELL_VAR,
+                                 K=N_COMPRESS, workspace=ws, out_device=True)
+
+    # ---- kernel-resident throughput ------------------------------------------------------
+    resident = apply.Targets.full(cat["fluxes"], cat["fluxes_var"], cat["z"]).to_device()
+    for _ in range(args.warmup):
+        step_resident(resident)
+    barrier()
+    sampler = ClockSampler(local).start() if rank == 0 else None
+    L.dl_timing_enable(1)
+    launches0 = L.dl_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_resident(resident)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    kms, kn = ctypes.c_double(0), ctypes.c_int(0)
+    L.dl_timing_collect(ctypes.byref(kms), ctypes.byref(kn))
+    L.dl_timing_enable(0)
+    launches = L.dl_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    value = world * nO * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the public API with host buffers --------------------------------
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_flux, h_var = pin(cat["fluxes"]), pin(cat["fluxes_var"])
+    h_pdf = torch.empty((nO, nz), dtype=torch.float64).pin_memory()
+    h_idx = torch.empty((nO, N_COMPRESS), dtype=torch.int64).pin_memory()
+    h_ev = torch.empty((nO, N_COMPRESS), dtype=torch.float64).pin_memory()
+
+    def step_e2e():
+        tg = apply.Targets.full(h_flux.numpy(), h_var.numpy())
+        tg._dev = {tuple(range(nB)): (h_flux.cuda(non_blocking=True),
+                                      h_var.cuda(non_blocking=True), None)}
+        out = step_resident(tg)
+        if world > 1:          # gather to rank 0 like the (commented) Gatherv calls, :201-217
+            bufs = [torch.empty_like(out["pdf"]) for _ in range(world)] if rank == 0 else None
+            dist.gather(out["pdf"], bufs, dst=0)
+            ib = [torch.empty_like(out["top_idx"]) for _ in range(world)] if rank == 0 else None
+            dist.gather(out["top_idx"], ib, dst=0)
+            eb = [torch.empty_like(out["top_ev"]) for _ in range(world)] if rank == 0 else None
+            dist.gather(out["top_ev"], eb, dst=0)
+        h_pdf.copy_(out["pdf"], non_blocking=True)
+        h_idx.copy_(out["top_idx"], non_blocking=True)
+        h_ev.copy_(out["top_ev"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    step_e2e()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = world * nO * args.steps / (float(ms2.item()) * 1e-3)
+    h2d = h_flux.numel() * 8 + h_var.numel() * 8
+    d2h = h_pdf.numel() * 8 + h_idx.numel() * 8 + h_ev.numel() * 8
+
+    if rank == 0:
+        peaks = measured_peaks()
+        fp64 = ctypes.c_double(0)
+        L.dl_fp64_peak(5, ctypes.byref(fp64))
+        cells_per_launch = float(nO) * nT * nz * args.steps / max(kn.value, 1)
+        k_ms = kms.value / max(kn.value, 1)
+        achieved = cells_per_launch * FLOP_PER_CELL(nB) / (k_ms * 1e-3) * 1e-12
+        grid_bytes = grid.grid.numel() * 8 + prior.numel() * 8
+        roofline = {
+            "bound": "fp64", "kernel": "fused_like_kernel<%d,false>" % nB,
+            "achieved": achieved, "peak": fp64.value, "unit": "TFLOP/s",
+            "frac": achieved / fp64.value if fp64.value else None,
+            "peak_source": "measured live: dl_fp64_peak (dependent FMA chains, all SMs); "
+                           "MEASURED_PEAKS.json has no FP64 entry; datasheet 37.2 TFLOP/s",
+            "flop_per_cell": FLOP_PER_CELL(nB), "cells_per_launch": cells_per_launch,
+            "kernel_ms": k_ms, "kernel_share_of_step": kms.value / ms_total,
+            "traffic": None,
+            "hbm_algorithmic_GBs": grid_bytes * (kn.value / args.steps) / (ms_total / args.steps
+                                                                          * 1e-3) * 1e-9,
+            "hbm_peak_GBs": peaks.get("hbm_gbs"),
+        }
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline_sample(data, nT, nB)
+        line = {
+            "metric": "galaxy-PDFs/sec", "value": value, "unit": "galaxies/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(nO, nT, nz, nB),
+                       "targets_per_gpu": nO, "n_train": nT, "nz": nz, "bands": nB,
+                       "Ncompress": N_COMPRESS, "model_grid": "stand-in (template x smooth "
+                       "perturbation), replicated per GPU, %.2f GB" % (grid_bytes / 1e9),
+                       "l2": "inputs larger than L2 (model grid %.2f GB re-streamed per step)"
+                             % (grid_bytes / 1e9),
+                       "parallelism": "targets sharded by rank, no data-path collective"},
+            "e2e": {"value": e2e_value, "unit": "galaxies/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--targets", type=int, default=N_TARGETS, help="targets per GPU per step")
+    ap.add_argument("--train", type=int, default=N_TRAIN)
+    ap.add_argument("--ref-targets", type=int, default=8,
+                    help="reference arm: targets per step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,289 @@
+"""Batched, fused apply path: the B200 replacement of the per-target host loop of
+scripts/delight-apply.py:114-170.
+
+    grid  = ModelGrid.from_legacy(model_mean, model_covar)      # [nz, nT, nB] arrays of the script
+    prior = grid.gaussian_prior(redshiftGrid, train_z, sigma)   # delight-apply.py:104
+    out   = apply_fused(grid, prior, redshiftGrid, targets, ell_hat=1.0, ell_var=s**2, K=50)
+
+Everything numeric happens in libdelight_b200.so; torch is used for device memory, streams and
+index plumbing (gather/scatter of target rows) only.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+FUSED_MAX_BANDS = 8
+
+
+def partition(n, rank, size):
+    """Contiguous rank range with the reference's formula (scripts/delight-apply.py:50-53)."""
+    first = int(rank * n / float(size))
+    last = int(min(n, (rank + 1) * n / float(size)))
+    return first, last
+
+
+class Targets:
+    """Target catalogue in packed form: per target the list of valid bands (io.py:331-337) and
+    the fluxes / variances in those bands, left-packed into [nO, nB] arrays."""
+
+    def __init__(self, fluxes, fluxes_var, bands, nf, ztrue=None):
+        self.fluxes = np.ascontiguousarray(fluxes, dtype=np.float64)
+        self.fluxes_var = np.ascontiguousarray(fluxes_var, dtype=np.float64)
+        self.bands = np.ascontiguousarray(bands, dtype=np.int64)
+        self.nf = np.ascontiguousarray(nf, dtype=np.int64)
+        self.ztrue = None if ztrue is None else np.ascontiguousarray(ztrue, dtype=np.float64)
+        if self.fluxes.ndim != 2 or self.fluxes.shape != self.fluxes_var.shape or \
+                self.bands.shape != self.fluxes.shape or self.nf.shape != (self.fluxes.shape[0],):
+            raise ValueError("Targets: fluxes, fluxes_var, bands must be [nO, nB]; nf [nO]")
+        if self.nf.size and (self.nf.min() < 1 or self.nf.max() > self.fluxes.shape[1]):
+            raise ValueError("Targets: nf must be in [1, nB]")
+
+    @classmethod
+    def full(cls, fluxes, fluxes_var, ztrue=None):
+        """All targets observed in all nB bands."""
+        nO, nB = np.shape(fluxes)
+        return cls(fluxes, fluxes_var, np.tile(np.arange(nB), (nO, 1)), np.full(nO, nB), ztrue)
+
+    def __len__(self):
+        return self.fluxes.shape[0]
+
+    def slice(self, first, last):
+        return Targets(self.fluxes[first:last], self.fluxes_var[first:last],
+                       self.bands[first:last], self.nf[first:last],
+                       None if self.ztrue is None else self.ztrue[first:last])
+
+    def to_device(self):
+        """Upload fluxes / variances once (per band group); later apply_fused calls on this
+        object start from HBM-resident inputs."""
+        torch = _lib.require_cuda()
+        self._dev = {}
+        for bands, idx in self.groups():
+            nf = len(bands)
+            self._dev[bands] = (
+                torch.from_numpy(np.ascontiguousarray(self.fluxes[idx, :nf])).cuda(),
+                torch.from_numpy(np.ascontiguousarray(self.fluxes_var[idx, :nf])).cuda(),
+                torch.from_numpy(idx).cuda())
+        return self
+
+    def groups(self):
+        """Yield (band tuple, indices) for targets sharing the same band list."""
+        if getattr(self, "_groups", None) is not None:
+            for g in self._groups:
+                yield g
+            return
+        self._groups = list(self._compute_groups())
+        for g in self._groups:
+            yield g
+
+    def _compute_groups(self):
+        nO, nB = self.fluxes.shape
+        key = np.where(np.arange(nB)[None, :] < self.nf[:, None], self.bands, -1)
+        uniq, inv = np.unique(key, axis=0, return_inverse=True)
+        inv = inv.reshape(-1)
+        for g in range(uniq.shape[0]):
+            bands = tuple(int(b) for b in uniq[g] if b >= 0)
+            yield bands, np.nonzero(inv == g)[0]
+
+
+class ModelGrid:
+    """Per-training-galaxy flux predictions over the fine redshift grid, resident in HBM in the
+    fused kernel's layout [nT][2*nB][nzp] (rows 0..nB-1 means, nB..2nB-1 variances, z contiguous,
+    nzp = nz padded to the 128-redshift chunk)."""
+
+    def __init__(self, grid, nT, nB, nz):
+        self.grid, self.nT, self.nB, self.nz = grid, int(nT), int(nB), int(nz)
+        self.nzp = int(_lib.lib().dl_fused_padded_nz(self.nz))
+
+    @classmethod
+    def from_legacy(cls, model_mean, model_covar):
+        """From the script's arrays model_mean/model_covar [nz, nT, nB] (delight-apply.py:84-85),
+        NumPy (uploaded) or CUDA tensors."""
+        torch = _lib.require_cuda()
+        mm = _as_dev(model_mean)
+        mc = _as_dev(model_covar)
+        if mm.ndim != 3 or mm.shape != mc.shape:
+            raise ValueError("model_mean / model_covar must both be [nz, nT, nB]")
+        nz, nT, nB = mm.shape
+        nzp = int(_lib.lib().dl_fused_padded_nz(nz))
+        grid = torch.empty((nT, 2 * nB, nzp), dtype=torch.float64, device="cuda")
+        _lib.check(_lib.lib().dl_relayout_grid_dev(nz, nT, nB, _lib.ptr(mm), _lib.ptr(mc),
+                                                  _lib.ptr(grid), _lib.stream_ptr()))
+        return cls(grid, nT, nB, nz)
+
+    def gaussian_prior(self, zgrid, train_z, sigma):
+        """prior[t][z] = exp(-((z - z_t)/sigma)^2 / 2)  (delight-apply.py:104) -> [nT][nzp]."""
+        torch = _lib.require_cuda()
+        zg, zt = _as_dev(zgrid), _as_dev(train_z)
+        if zg.numel() != self.nz or zt.numel() != self.nT:
+            raise ValueError("gaussian_prior: zgrid [nz], train_z [nT]")
+        prior = torch.empty((self.nT, self.nzp), dtype=torch.float64, device="cuda")
+        _lib.check(_lib.lib().dl_zprior_dev(self.nT, self.nz, _lib.ptr(zg), _lib.ptr(zt),
+                                           float(sigma), _lib.ptr(prior), _lib.stream_ptr()))
+        return prior
+
+    def explicit_prior(self, prior_zt):
+        """From an explicit prior[nz, nT] (e.g. scripts/templateFitting.py:79-82)."""
+        torch = _lib.require_cuda()
+        p = _as_dev(prior_zt)
+        if tuple(p.shape) != (self.nz, self.nT):
+            raise ValueError("explicit_prior: expected [nz, nT]")
+        prior = torch.empty((self.nT, self.nzp), dtype=torch.float64, device="cuda")
+        _lib.check(_lib.lib().dl_relayout_prior_dev(self.nz, self.nT, _lib.ptr(p),
+                                                   _lib.ptr(prior), _lib.stream_ptr()))
+        return prior
+
+
+def _as_dev(a):
+    torch = _lib.require_cuda()
+    if isinstance(a, torch.Tensor):
+        t = a
+        if t.dtype != torch.float64:
+            raise ValueError("expected float64")
+        return t.cuda().contiguous()
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return torch.from_numpy(a).cuda()
+
+
+def _pick_nsplit(n_targets, nchunk, nT, sm_count):
+    ctas = nchunk * ((n_targets + 31) // 32)
+    want = 2 * sm_count          # 2 resident CTAs per SM
+    if ctas >= want:
+        return 1
+    return int(max(1, min((want + ctas - 1) // ctas, max(1, nT // 32), 64)))
+
+
+class FusedWorkspace:
+    """Re-usable device scratch for apply_fused (evidence partials dominate:
+    16 B x n_chunks x tile targets x nT)."""
+
+    def __init__(self, max_bytes=None):
+        torch = _lib.require_cuda()
+        if max_bytes is None:
+            free, _ = torch.cuda.mem_get_info()
+            max_bytes = min(int(free * 0.5), 48 << 30)
+        self.max_bytes = int(max_bytes)
+        self.buf = None
+        self._sm = None
+
+    def sm_count(self):
+        if self._sm is None:
+            sm = ctypes.c_int(0)
+            _lib.check(_lib.lib().dl_device_info(ctypes.byref(sm), None, None, None))
+            self._sm = sm.value
+        return self._sm
+
+    def get(self, nbytes):
+        torch = _lib.require_cuda()
+        if self.buf is None or self.buf.numel() < nbytes:
+            self.buf = None
+            self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device="cuda")
+        return self.buf
+
+    def tile_size(self, nO, nT, nz, nsplit_hint=1):
+        L = _lib.lib()
+        per32 = L.dl_fused_workspace_bytes(32, nT, nz, nsplit_hint, 0)
+        tile = max(32, (self.max_bytes // max(per32, 1)) * 32)
+        return int(min(tile, (nO + 31) // 32 * 32))
+
+
+def apply_fused(grid, prior, zgrid, targets, ell_hat=1.0, ell_var=1.0, K=0, want_evid=False,
+                want_metrics=False, workspace=None, nsplit=None, out_device=False):
+    """Likelihood + PDF + evidences + top-K for all `targets` against the whole model grid.
+
+    ell_hat / ell_var: scalars (what delight-apply.py:119-144 passes: 1 and ellPriorSigma^2) or
+    arrays [nz] (the general operator signature, utils_cy.pyx:92-93).
+    Returns dict(pdf [nO, nz], top_idx [nO, K] int64, top_ev [nO, K], evid [nO, nT] | None,
+    metrics [nO, 8] | None) as NumPy arrays (or CUDA tensors with out_device=True).
+    """
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    nO = len(targets)
+    nT, nB, nz = grid.nT, grid.nB, grid.nz
+    if targets.fluxes.shape[1] > nB and targets.bands.max() >= nB:
+        raise ValueError("target band index outside the model grid")
+    if K > nT:
+        raise ValueError("Ncompress (K=%d) exceeds the number of training galaxies (%d)" % (K, nT))
+    ws = workspace or FusedWorkspace()
+    zg = _as_dev(zgrid)
+    zdep = np.ndim(ell_hat) > 0 or np.ndim(ell_var) > 0
+    if zdep:
+        eh = _as_dev(np.broadcast_to(np.asarray(ell_hat, dtype=np.float64), (nz,)))
+        ev = _as_dev(np.broadcast_to(np.asarray(ell_var, dtype=np.float64), (nz,)))
+        ehs = evs = 1.0
+    else:
+        eh = ev = None
+        ehs, evs = float(ell_hat), float(ell_var)
+
+    pdf = torch.empty((nO, nz), dtype=torch.float64, device="cuda")
+    top_idx = torch.empty((nO, K), dtype=torch.int64, device="cuda") if K > 0 else None
+    top_ev = torch.empty((nO, K), dtype=torch.float64, device="cuda") if K > 0 else None
+    evid = torch.empty((nO, nT), dtype=torch.float64, device="cuda") if want_evid else None
+    nchunk = grid.nzp // L.dl_fused_chunk()
+    launches = 0
+
+    for bands, idx in targets.groups():
+        nf = len(bands)
+        if nf > FUSED_MAX_BANDS:
+            raise _lib.DelightB200Error("fused likelihood supports up to %d bands per target, "
+                                        "got %d" % (FUSED_MAX_BANDS, nf))
+        single = idx.size == nO
+        cached = getattr(targets, "_dev", None)
+        if cached is not None and bands in cached:
+            obs, var, didx = cached[bands]
+        else:
+            obs_h = targets.fluxes[idx, :nf] if not single else targets.fluxes[:, :nf]
+            var_h = targets.fluxes_var[idx, :nf] if not single else targets.fluxes_var[:, :nf]
+            obs = torch.from_numpy(np.ascontiguousarray(obs_h)).cuda(non_blocking=True)
+            var = torch.from_numpy(np.ascontiguousarray(var_h)).cuda(non_blocking=True)
+            didx = None
+        bands_c = (ctypes.c_int * nf)(*bands)
+        n_g = idx.size
+        if single:
+            g_pdf, g_idx, g_ev, g_evid = pdf, top_idx, top_ev, evid
+        else:
+            g_pdf = torch.empty((n_g, nz), dtype=torch.float64, device="cuda")
+            g_idx = torch.empty((n_g, K), dtype=torch.int64, device="cuda") if K > 0 else None
+            g_ev = torch.empty((n_g, K), dtype=torch.float64, device="cuda") if K > 0 else None
+            g_evid = torch.empty((n_g, nT), dtype=torch.float64, device="cuda") \
+                if want_evid else None
+        ns_hint = nsplit or _pick_nsplit(n_g, nchunk, nT, ws.sm_count())
+        tile = ws.tile_size(n_g, nT, nz, ns_hint)
+        for t0 in range(0, n_g, tile):
+            n = min(tile, n_g - t0)
+            ns = nsplit or _pick_nsplit(n, nchunk, nT, ws.sm_count())
+            nbytes = L.dl_fused_workspace_bytes(n, nT, nz, ns, int(want_evid or K == 0))
+            buf = ws.get(nbytes)
+            _lib.check(L.dl_like_fused_dev(
+                n, nT, nz, nB, nf, bands_c, _lib.ptr(obs[t0:t0 + n]), _lib.ptr(var[t0:t0 + n]),
+                _lib.ptr(grid.grid), _lib.ptr(prior), _lib.ptr(zg), ehs, evs, _lib.ptr(eh),
+                _lib.ptr(ev), ns, K, _lib.ptr(g_pdf[t0:t0 + n]), nz,
+                _lib.ptr(g_evid[t0:t0 + n]) if g_evid is not None else None,
+                _lib.ptr(g_idx[t0:t0 + n]) if K > 0 else None,
+                _lib.ptr(g_ev[t0:t0 + n]) if K > 0 else None,
+                _lib.ptr(buf), buf.numel(), _lib.stream_ptr()))
+            launches += 1
+        if not single:
+            if didx is None:
+                didx = torch.from_numpy(idx).cuda()
+            pdf.index_copy_(0, didx, g_pdf)
+            if K > 0:
+                top_idx.index_copy_(0, didx, g_idx)
+                top_ev.index_copy_(0, didx, g_ev)
+            if want_evid:
+                evid.index_copy_(0, didx, g_evid)
+
+    metrics = None
+    if want_metrics:
+        zt = _as_dev(targets.ztrue) if targets.ztrue is not None else None
+        metrics = torch.empty((nO, 8), dtype=torch.float64, device="cuda")
+        _lib.check(L.dl_metrics_dev(nO, nz, _lib.ptr(pdf), nz, _lib.ptr(zg), _lib.ptr(zt),
+                                    _lib.ptr(metrics), _lib.stream_ptr()))
+    out = dict(pdf=pdf, top_idx=top_idx, top_ev=top_ev, evid=evid, metrics=metrics,
+               fused_launches=launches)
+    if not out_device:
+        for k, v in list(out.items()):
+            if isinstance(v, torch.Tensor):
+                out[k] = v.cpu().numpy()
+    return out

@@ -1,0 +1,159 @@
+// Shared device helpers for the delight_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#define DL_OK 0
+#define DL_ERR_INVALID 1
+#define DL_ERR_CUDA 2
+#define DL_ERR_NOMEM 3
+#define DL_ERR_UNSUPPORTED 4
+
+void dl_set_error(const char* fmt, ...);
+void dl_count_launch(int n = 1);                    // bookkeeping: kernels launched by this library
+bool dl_timing_enabled();
+void dl_timing_mark(cudaStream_t stream, int which);  // 0 = before, 1 = after the fused kernel
+
+#define DL_CUDA_CHECK(expr)                                                              \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            dl_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr,                   \
+                         cudaGetErrorString(_e));                                        \
+            return DL_ERR_CUDA;                                                          \
+        }                                                                                \
+    } while (0)
+
+#define DL_REQUIRE(cond, msg)                                                            \
+    do {                                                                                 \
+        if (!(cond)) {                                                                   \
+            dl_set_error("%s:%d: invalid argument: %s", __FILE__, __LINE__, msg);        \
+            return DL_ERR_INVALID;                                                       \
+        }                                                                                \
+    } while (0)
+
+#define DL_TWO_PI 6.283185307179586476925286766559
+
+namespace dl {
+
+// ------------------------------------------------------------------ FP64 fast-path arithmetic
+// MUFU.RCP64H seed (~20 bits) + two Newton steps on the FP64 pipe.  Valid for normal, positive
+// finite inputs (variances, sums of squares); no special-case branches.  ~1 ulp.
+__device__ __forceinline__ double rcp_fast(double d) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    double e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-d, x, 1.0);
+    x = fma(x, e, x);
+    return x;
+}
+
+// MUFU.RSQ64H seed + two coupled Newton steps.  Same validity domain as rcp_fast.
+__device__ __forceinline__ double rsqrt_fast(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double g = d * y;           // ~sqrt(d)
+    double h = 0.5 * y;         // ~1/(2 sqrt(d))
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    h = fma(h, r, h);
+    return h + h;
+}
+
+// exp(x) for x <= 0 (-inf / x < -708 -> 0: results that would be denormal are flushed; NaN
+// propagates).  Range reduction x = n ln2 + r, |r| <= ln2/2, degree-11 Taylor polynomial
+// (truncation 6e-15 relative, far below the 1e-9 parity contract), scaling through the
+// exponent field.
+__device__ __forceinline__ double exp_nonpos(double x) {
+    const double L2E = 1.4426950408889634074;
+    const double LN2_HI = 6.93147180369123816490e-01;
+    const double LN2_LO = 1.90821492927058770002e-10;
+    const double SHIFT = 6755399441055744.0;  // 1.5 * 2^52
+    double t = fma(x, L2E, SHIFT);
+    int n = __double2loint(t);
+    double fn = t - SHIFT;
+    double r = fma(-fn, LN2_HI, x);
+    r = fma(-fn, LN2_LO, r);
+    double p = 2.50521083854417187751e-08;             // 1/11!
+    p = fma(p, r, 2.75573192239858906526e-07);         // 1/10!
+    p = fma(p, r, 2.75573192239858906526e-06);         // 1/9!
+    p = fma(p, r, 2.48015873015873015873e-05);         // 1/8!
+    p = fma(p, r, 1.98412698412698412698e-04);         // 1/7!
+    p = fma(p, r, 1.38888888888888888889e-03);         // 1/6!
+    p = fma(p, r, 8.33333333333333333333e-03);         // 1/5!
+    p = fma(p, r, 4.16666666666666666667e-02);         // 1/4!
+    p = fma(p, r, 1.66666666666666666667e-01);         // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    // scale by 2^n through the exponent bits; results below 2^-1021 flush to zero
+    int hi = __double2hiint(p) + (n << 20);
+    double res = __hiloint2double(hi, __double2loint(p));
+    return (x >= -708.0) ? res : ((x != x) ? x : 0.0);
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, s));
+    return v;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    return v;
+}
+
+// ------------------------------------------------------------------ mbarrier + TMA bulk copy
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// 1-D TMA bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP).
+// dst/src 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem,
+                                             uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+}  // namespace dl

@@ -1,0 +1,109 @@
+// Non-fused likelihood: the drop-in for delight/utils_cy.pyx:83-128 (one target per call, the
+// full like[nz][nt] array is returned in the reference's layout).  HBM-bound by construction:
+// 2*nf*8 B read + 8 B written per cell, so the literal formulas (divisions, logs) are kept and
+// the kernel is organised for coalescing only: one thread per (z, t) cell, nf contiguous
+// doubles per thread, cells contiguous across the warp.
+#include "common.cuh"
+
+namespace dl {
+
+__device__ __forceinline__ unsigned long long dkey(double v) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dkey_inv(unsigned long long k) {
+    unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+// log-likelihood per cell (utils_cy.pyx:98-118) + global max (:120-124) via ordered atomicMax
+__global__ void __launch_bounds__(256) loglike_kernel(
+    long long ncell, int nt, int nf, const double* __restrict__ f_obs,
+    const double* __restrict__ f_obs_var, const double* __restrict__ f_mod,
+    const double* __restrict__ f_mod_covar, const double* __restrict__ ell_hat,
+    const double* __restrict__ ell_var, double* __restrict__ like,
+    unsigned long long* __restrict__ maxkey) {
+    extern __shared__ double sh[];                 // f_obs[nf], f_obs_var[nf]
+    for (int i = threadIdx.x; i < nf; i += blockDim.x) { sh[i] = f_obs[i]; sh[nf + i] = f_obs_var[i]; }
+    __syncthreads();
+    double best = -INFINITY;
+    for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < ncell;
+         cell += (long long)gridDim.x * blockDim.x) {
+        const long long iz = cell / nt;
+        const double eh = ell_hat[iz], ev = ell_var[iz];
+        const double* m = f_mod + cell * nf;
+        const double* c = f_mod_covar + cell * nf;
+        double ell = 0.0, fot = 0.0, ftt = 0.0, foo = 0.0, logden = 0.0;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            fot = eh / ev; ftt = 1.0 / ev; foo = eh * eh / ev; logden = 0.0;
+            for (int k = 0; k < nf; ++k) {
+                const double mk = m[k];
+                const double var = sh[nf + k] + ell * ell * c[k];
+                fot += mk * sh[k] / var;
+                ftt += mk * mk / var;
+                foo += sh[k] * sh[k] / var;
+                if (pass == 1) logden += log(var * DL_TWO_PI);
+            }
+            ell = fot / ftt;
+        }
+        const double chi2 = foo - fot * fot / ftt;
+        logden += log(DL_TWO_PI * ev) + log(ftt / DL_TWO_PI);
+        const double L = -0.5 * chi2 - 0.5 * logden;
+        like[cell] = L;
+        best = fmax(best, L);
+    }
+    best = warp_max(best);
+    __shared__ double wbest[8];
+    if ((threadIdx.x & 31) == 0) wbest[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) best = fmax(best, wbest[w]);
+        atomicMax(maxkey, dkey(best));
+    }
+}
+
+// like = exp(like - max)  (utils_cy.pyx:125-128)
+__global__ void __launch_bounds__(256) expnorm_kernel(long long ncell, double* __restrict__ like,
+                                                      const unsigned long long* __restrict__ maxkey) {
+    const double top = dkey_inv(*maxkey);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ncell;
+         i += (long long)gridDim.x * blockDim.x)
+        like[i] = exp(like[i] - top);
+}
+
+}  // namespace dl
+
+using namespace dl;
+
+extern "C" {
+
+// Device-pointer form of approx_flux_likelihood_cy.  `scratch` = 8 bytes of device memory.
+int dl_approx_flux_likelihood_dev(double* like, long long nz, long long nt, long long nf,
+                                  const double* f_obs, const double* f_obs_var,
+                                  const double* f_mod, const double* f_mod_covar,
+                                  const double* ell_hat, const double* ell_var, void* scratch,
+                                  void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DL_REQUIRE(nz >= 0 && nt >= 0 && nf >= 0, "negative size");
+    DL_REQUIRE(nf <= 1024, "nf too large");
+    const long long ncell = nz * nt;
+    if (ncell == 0) return DL_OK;
+    DL_REQUIRE(like && f_obs && f_obs_var && f_mod && f_mod_covar && ell_hat && ell_var && scratch,
+               "null pointer");
+    DL_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 8, stream));
+    long long blocks = (ncell + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    loglike_kernel<<<(unsigned)blocks, 256, 2 * nf * sizeof(double), stream>>>(
+        ncell, (int)nt, (int)nf, f_obs, f_obs_var, f_mod, f_mod_covar, ell_hat, ell_var, like,
+        (unsigned long long*)scratch);
+    DL_CUDA_CHECK(cudaGetLastError());
+    dl_count_launch();
+    expnorm_kernel<<<(unsigned)blocks, 256, 0, stream>>>(ncell, like,
+                                                         (const unsigned long long*)scratch);
+    DL_CUDA_CHECK(cudaGetLastError());
+    dl_count_launch();
+    return DL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,818 @@
+// Fused photo-z likelihood for a batch of targets (subsystem 1 of the north star).
+//
+// Replaces the per-target host loop of scripts/delight-apply.py:114-162:
+//     approx_flux_likelihood_cy (delight/utils_cy.pyx:83-128)  ->  like[nz][nT]
+//     like *= prior; pdf = sum_t like; evid = trapz_z like; top-K by evidence
+// with one launch over (z-chunk x target-tile x training-range).  The like[nz][nT] array of a
+// target never exists in HBM.
+//
+// Work decomposition (B200: 148 SMs, FP64 pipe = 16 lanes / SMSP, 227 KB smem / SM)
+//   CTA      = 8 warps (lane 0 of warp 0 also drives TMA); 2 CTAs / SM (96 KB smem, <=128 regs)
+//   CTA tile = one z-chunk of 128 redshifts  x  32 targets (4 per compute warp)
+//              x  a contiguous range of training galaxies (all of them unless nsplit > 1)
+//   lane     = 4 redshifts of the chunk (z = z0 + 32*j + lane) -> conflict-free smem rows
+//   producer = per training galaxy one pipeline stage: 2*NF+1 rows (NF band means, NF band
+//              variances, the prior row) of 128 doubles each, fetched with 1-D TMA bulk copies
+//              (cp.async.bulk ... mbarrier::complete_tx) into a 4-deep full/empty mbarrier ring
+//   compute  = per (target, training galaxy, z) cell, all in FP64 on the vector pipe:
+//              pass 0 with the observed variances only (2 FMA / band, per-target constants
+//              broadcast from smem), one reciprocal for the luminosity scale, pass 1 with the
+//              model variance folded in (1 reciprocal + 6 FMA-class ops / band), then
+//              chi2, (prod var * FTT)^-1/2 by one rsqrt, one exp.  No log, no division.
+//
+// Normalisation.  The reference subtracts the GLOBAL max log-likelihood of a target before
+// exp (utils_cy.pyx:120-128).  Here every warp keeps, per target, a lazily updated reference
+// exponent R (running max of -chi2/2 over what the warp has seen) and the running max V of the
+// un-priored value exp(-chi2/2 - R) / sqrt(det); accumulators are rescaled on the rare update.
+// A finalize pass combines the (R, V) of all warps of a target and rescales pdf / evidences, so
+// results equal exp(L - max L) up to rounding; per-target constant factors cancel and are never
+// computed.  All variances are pre-scaled by a per-target power of two c (exact) so products
+// over bands stay in range.
+#include "common.cuh"
+
+namespace dl {
+
+constexpr int FW = 8;             // compute warps per CTA
+constexpr int FTO = 4;            // targets per compute warp
+constexpr int FZT = 4;            // redshifts per lane
+constexpr int FZC = 32 * FZT;     // redshifts per CTA chunk
+constexpr int FSTAGES = 4;        // TMA ring depth
+constexpr int FTPC = FW * FTO;    // targets per CTA
+constexpr int FTHREADS = FW * 32;
+constexpr int MAXNF = 8;
+
+__host__ __device__ constexpr int tc_stride(int nf) { return (5 * nf + 6 + 1) & ~1; }
+
+struct FusedParams {
+    const double* grid;    // [nT][2*nB][nzp]  rows 0..nB-1 mean, nB..2nB-1 variance
+    const double* prior;   // [nT][nzp]
+    const double* tconst;  // [nO][tc_stride(NF)]
+    const double* wz;      // [nzp] trapezoid weights (0 in the padding)
+    const double* zdep;    // [4][nzp]: ell_hat/ell_var, 1/ell_var, ell_hat^2/ell_var, ell_var
+    double* pdf_part;      // [nsplit][nO][nzp]
+    double2* evid_part;    // [nchunk][nO][nT]  (E, R)
+    double* Rw;            // [nsplit][nchunk][nO]
+    double* Vw;            // [nsplit][nchunk][nO]
+    int bands[MAXNF];
+    int nB, nz, nzp, nT, nO, nchunk, nsplit;
+};
+
+template <int NF, bool ZDEP>
+__global__ void __launch_bounds__(FTHREADS, 2) fused_like_kernel(const FusedParams p) {
+    constexpr int ROWS = 2 * NF + 1;
+    constexpr int TCS = tc_stride(NF);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* stage = reinterpret_cast<double*>(smem_raw);        // [FSTAGES][ROWS][FZC]
+    double* pdf_sm = stage + FSTAGES * ROWS * FZC;              // [FTPC][FZC]
+    double* tc_sm = pdf_sm + FTPC * FZC;                        // [FTPC][TCS]
+    double* wz_sm = tc_sm + FTPC * TCS;                         // [FZC]
+    double* zd_sm = wz_sm + FZC;                                // [4][FZC] (ZDEP only)
+    uint64_t* full = reinterpret_cast<uint64_t*>(zd_sm + (ZDEP ? 4 * FZC : 0));
+    uint64_t* empty = full + FSTAGES;
+
+    const int chunk = blockIdx.x % p.nchunk;
+    const int otile = blockIdx.x / p.nchunk;
+    const int split = blockIdx.y;
+    const int z0 = chunk * FZC;
+    const int t_begin = (int)(((long long)split * p.nT) / p.nsplit);
+    const int t_end = (int)(((long long)(split + 1) * p.nT) / p.nsplit);
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < FSTAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], FW);
+        }
+        mbar_fence_init();
+    }
+    for (int i = threadIdx.x; i < FTPC * TCS; i += FTHREADS) {
+        int o = otile * FTPC + i / TCS;
+        o = o < p.nO ? o : p.nO - 1;
+        tc_sm[i] = p.tconst[(size_t)o * TCS + (i % TCS)];
+    }
+    for (int i = threadIdx.x; i < FTPC * FZC; i += FTHREADS) pdf_sm[i] = 0.0;
+    for (int i = threadIdx.x; i < FZC; i += FTHREADS) {
+        wz_sm[i] = p.wz[z0 + i];
+        if (ZDEP) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) zd_sm[k * FZC + i] = p.zdep[(size_t)k * p.nzp + z0 + i];
+        }
+    }
+    __syncthreads();
+
+    // ---------------------------------------------------------------------- TMA producer
+    // Lane 0 of warp 0 doubles as the producer: before computing step `it` it refills the stage
+    // that every warp released two steps ago (prefetch distance FSTAGES-2 steps, so it does not
+    // wait on warps that are still inside the previous step).
+    const int nsteps = t_end - t_begin;
+    auto issue_stage = [&](int step) {
+        const int s = step % FSTAGES;
+        const uint32_t ph = (step / FSTAGES) & 1;
+        const size_t row = (size_t)p.nzp;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full[s], ROWS * FZC * sizeof(double));
+        const double* gt = p.grid + (size_t)(t_begin + step) * 2 * p.nB * row + z0;
+        double* dst = stage + s * ROWS * FZC;
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            tma_bulk_g2s(dst + f * FZC, gt + (size_t)p.bands[f] * row, FZC * sizeof(double),
+                         &full[s]);
+            tma_bulk_g2s(dst + (NF + f) * FZC, gt + (size_t)(p.nB + p.bands[f]) * row,
+                         FZC * sizeof(double), &full[s]);
+        }
+        tma_bulk_g2s(dst + 2 * NF * FZC, p.prior + (size_t)(t_begin + step) * row + z0,
+                     FZC * sizeof(double), &full[s]);
+    };
+    if (threadIdx.x == 0) {
+        for (int step = 0; step < FSTAGES - 2 && step < nsteps; ++step) issue_stage(step);
+    }
+
+    // ---------------------------------------------------------------------- compute warps
+    double R[FTO], V[FTO], E[FTO];
+#pragma unroll
+    for (int o = 0; o < FTO; ++o) { R[o] = -1e300; V[o] = 0.0; E[o] = 0.0; }
+    const double* tcw = tc_sm + warp * FTO * TCS;
+    double* pdfw = pdf_sm + warp * FTO * FZC;
+    const int og0 = otile * FTPC + warp * FTO;
+
+    int it = 0;
+    for (int t = t_begin; t < t_end; ++t, ++it) {
+        const int s = it % FSTAGES;
+        const uint32_t ph = (it / FSTAGES) & 1;
+        if (threadIdx.x == 0 && it + FSTAGES - 2 < nsteps) issue_stage(it + FSTAGES - 2);
+        __syncwarp();
+        mbar_wait(&full[s], ph);
+        const double* st = stage + s * ROWS * FZC;
+#pragma unroll 1
+        for (int zi = 0; zi < FZT; ++zi) {
+            const int zl = zi * 32 + lane;
+            double m[NF], cv[NF], m2[NF];
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                m[f] = st[f * FZC + zl];
+                cv[f] = st[(NF + f) * FZC + zl];
+                m2[f] = m[f] * m[f];
+            }
+            const double pr = st[2 * NF * FZC + zl];
+            const double wzv = wz_sm[zl];
+            const bool valid = (z0 + zl) < p.nz;
+            double zot = 0, ztt = 0, zoo = 0, zev = 1.0;
+            if (ZDEP) {
+                zot = zd_sm[zl]; ztt = zd_sm[FZC + zl]; zoo = zd_sm[2 * FZC + zl];
+                zev = zd_sm[3 * FZC + zl];
+            }
+#pragma unroll
+            for (int o = 0; o < FTO; ++o) {
+                const double* tc = tcw + o * TCS;
+                const double hc = tc[5 * NF + 0];
+                const double ic = tc[5 * NF + 1];
+                double pOT, pTT, pOO;
+                if (ZDEP) {
+                    const double c = tc[5 * NF + 5];
+                    pOT = c * zot; pTT = c * ztt; pOO = c * zoo;
+                } else {
+                    pOT = tc[5 * NF + 2]; pTT = tc[5 * NF + 3]; pOO = tc[5 * NF + 4];
+                }
+                // pass 0: observed variances only (utils_cy.pyx:101-113 with ellML = 0)
+                double fot = pOT, ftt = pTT;
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    fot = fma(m[f], tc[f], fot);
+                    ftt = fma(m2[f], tc[NF + f], ftt);
+                }
+                const double ell = fot * rcp_fast(ftt);
+                const double e2 = ell * (ell * ic);
+                // pass 1: variance inflated by ell^2 * model variance (utils_cy.pyx:107-112)
+                fot = pOT; ftt = pTT;
+                double foo = pOO, P = zev;
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    const double var = fma(e2, cv[f], tc[2 * NF + f]);
+                    const double r = rcp_fast(var);
+                    const double tm = m[f] * r;
+                    fot = fma(tm, tc[3 * NF + f], fot);
+                    ftt = fma(tm, m[f], ftt);
+                    foo = fma(tc[4 * NF + f], r, foo);
+                    P *= var;
+                }
+                const double y = rsqrt_fast(P * ftt);       // (det)^-1/2   (:111-117)
+                const double rF = (y * y) * P;              // 1 / FTT
+                const double chi2 = fma(-(fot * rF), fot, foo);  // :115
+                double x = hc * chi2;
+                x = valid ? x : -INFINITY;
+                double sarg = x - R[o];
+                if (__any_sync(0xffffffffu, sarg > 0.0)) {
+                    // rare: the warp met a better cell than its reference exponent
+                    const double xm = warp_max(x);
+                    const double fs = exp(R[o] - xm);
+                    R[o] = xm; V[o] *= fs; E[o] *= fs;
+#pragma unroll
+                    for (int zj = 0; zj < FZT; ++zj) pdfw[o * FZC + zj * 32 + lane] *= fs;
+                    sarg = x - xm;
+                }
+                const double v = exp_nonpos(sarg) * y;       // :118,128 up to the global scale
+                if (__any_sync(0xffffffffu, v > V[o])) V[o] = fmax(V[o], warp_max(v));
+                const double vp = v * pr;                    // delight-apply.py:145
+                pdfw[o * FZC + zl] += vp;                    // :147
+                E[o] = fma(vp, wzv, E[o]);                   // :148
+            }
+        }
+        // evidence of (target, training galaxy t) over this z-chunk
+#pragma unroll
+        for (int o = 0; o < FTO; ++o) E[o] = warp_sum(E[o]);
+        {
+            double ev = E[0], rr = R[0];
+#pragma unroll
+            for (int o = 1; o < FTO; ++o) if (lane == o) { ev = E[o]; rr = R[o]; }
+            const int og = og0 + lane;
+            if (lane < FTO && og < p.nO)
+                p.evid_part[((size_t)chunk * p.nO + og) * p.nT + t] = make_double2(ev, rr);
+        }
+#pragma unroll
+        for (int o = 0; o < FTO; ++o) E[o] = 0.0;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+    }
+
+#pragma unroll
+    for (int o = 0; o < FTO; ++o) {
+        const int og = og0 + o;
+        if (og < p.nO) {
+            double* dst = p.pdf_part + ((size_t)split * p.nO + og) * p.nzp + z0;
+#pragma unroll
+            for (int zj = 0; zj < FZT; ++zj) dst[zj * 32 + lane] = pdfw[o * FZC + zj * 32 + lane];
+            if (lane == 0) {
+                const size_t k = ((size_t)split * p.nchunk + chunk) * p.nO + og;
+                p.Rw[k] = R[o];
+                p.Vw[k] = V[o];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-target constants (see header comment): scaled by c = 2^round(mean log2 var)
+// in:  obs/var [nO][NF] (already restricted to the group's NF bands), ell_hat/ell_var scalars
+// out: tconst [nO][tc_stride(NF)] = a'(NF) w'(NF) var'(NF) obs(NF) obs^2(NF) hc ic pOT pTT pOO c
+__global__ void prep_targets_kernel(int nO, int NF, const double* __restrict__ obs,
+                                    const double* __restrict__ var, double ell_hat,
+                                    double ell_var, double* __restrict__ tconst) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= nO) return;
+    const int TCS = tc_stride(NF);
+    double* tc = tconst + (size_t)o * TCS;
+    double s = 0.0;
+    for (int f = 0; f < NF; ++f) s += log2(var[(size_t)o * NF + f]);
+    int k = (int)rint(s / NF);
+    k = k < -1000 ? -1000 : (k > 1000 ? 1000 : k);
+    const double c = ldexp(1.0, k), ic = ldexp(1.0, -k);
+    for (int f = 0; f < NF; ++f) {
+        const double ob = obs[(size_t)o * NF + f];
+        const double vs = var[(size_t)o * NF + f] * ic;
+        const double w = 1.0 / vs;
+        tc[f] = ob * w;
+        tc[NF + f] = w;
+        tc[2 * NF + f] = vs;
+        tc[3 * NF + f] = ob;
+        tc[4 * NF + f] = ob * ob;
+    }
+    tc[5 * NF + 0] = -0.5 * ic;
+    tc[5 * NF + 1] = ic;
+    tc[5 * NF + 2] = c * (ell_hat / ell_var);
+    tc[5 * NF + 3] = c / ell_var;
+    tc[5 * NF + 4] = c * (ell_hat * ell_hat / ell_var);
+    tc[5 * NF + 5] = c;
+    if (TCS > 5 * NF + 6) tc[5 * NF + 6] = 0.0;
+}
+
+// combine the per-warp (R, V) of each target: Rfin = max R, Vfin = max V * exp(R - Rfin)
+__global__ void finalize_scales_kernel(int nO, int nparts, const double* __restrict__ Rw,
+                                       const double* __restrict__ Vw, double* __restrict__ Rfin,
+                                       double* __restrict__ invV) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= nO) return;
+    double rmax = -INFINITY;
+    for (int k = 0; k < nparts; ++k) rmax = fmax(rmax, Rw[(size_t)k * nO + o]);
+    double vmax = 0.0;
+    for (int k = 0; k < nparts; ++k)
+        vmax = fmax(vmax, Vw[(size_t)k * nO + o] * exp(Rw[(size_t)k * nO + o] - rmax));
+    Rfin[o] = rmax;
+    invV[o] = 1.0 / vmax;
+}
+
+// pdf[o][z] = sum_split pdf_part * exp(R_part - Rfin) / Vfin     (out: [nO][ld_out])
+__global__ void finalize_pdf_kernel(int nO, int nz, int nzp, int nchunk, int nsplit,
+                                    const double* __restrict__ pdf_part,
+                                    const double* __restrict__ Rw,
+                                    const double* __restrict__ Rfin,
+                                    const double* __restrict__ invV, double* __restrict__ pdf,
+                                    long long ld_out) {
+    const int z = blockIdx.y * blockDim.x + threadIdx.x;
+    const int o = blockIdx.x;
+    if (z >= nz) return;
+    const int chunk = z / FZC;
+    double acc = 0.0;
+    for (int s = 0; s < nsplit; ++s) {
+        const double r = Rw[((size_t)s * nchunk + chunk) * nO + o];
+        acc += pdf_part[((size_t)s * nO + o) * nzp + z] * exp(r - Rfin[o]);
+    }
+    pdf[(size_t)o * ld_out + z] = acc * invV[o];
+}
+
+// evid[o][t] = sum_chunk E * exp(R - Rfin) / Vfin
+__global__ void finalize_evid_kernel(int nO, int nT, int nchunk,
+                                     const double2* __restrict__ evid_part,
+                                     const double* __restrict__ Rfin,
+                                     const double* __restrict__ invV,
+                                     double* __restrict__ evid) {
+    const int t = blockIdx.y * blockDim.x + threadIdx.x;
+    const int o = blockIdx.x;
+    if (t >= nT) return;
+    const double rf = Rfin[o];
+    double acc = 0.0;
+    for (int c = 0; c < nchunk; ++c) {
+        const double2 e = evid_part[((size_t)c * nO + o) * nT + t];
+        acc += e.x * exp(e.y - rf);
+    }
+    evid[(size_t)o * nT + t] = acc * invV[o];
+}
+
+// ------------------------------------------------------------------------------------------
+// top-K training galaxies per target by evidence (scripts/delight-apply.py:150-153).
+// Order: descending evidence, equal evidences -> larger index first
+// (= np.argsort(kind='stable')[::-1]).  One CTA per target:
+// 8 x 8-bit radix-select passes over the order-preserving 64-bit keys, gather, bitonic sort.
+constexpr int TK_THREADS = 256;
+constexpr int TK_MAXK = 1024;
+
+__device__ __forceinline__ unsigned long long order_key(double v) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__global__ void __launch_bounds__(TK_THREADS) topk_kernel(int nT, int K,
+                                                          const double* __restrict__ evid,
+                                                          long long* __restrict__ top_idx,
+                                                          double* __restrict__ top_ev) {
+    __shared__ unsigned int hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_need, s_count, s_eq_skip, s_run;
+    __shared__ unsigned int warp_tot[TK_THREADS / 32];
+    __shared__ unsigned long long skey[TK_MAXK];
+    __shared__ int sidx[TK_MAXK];
+
+    const int o = blockIdx.x;
+    const double* row = evid + (size_t)o * nT;
+    const int tid = threadIdx.x;
+
+    if (tid == 0) { s_prefix = 0ull; s_need = K; }
+    __syncthreads();
+    // radix select of the K-th largest key
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = 56 - 8 * pass;
+        hist[tid] = 0;   // TK_THREADS == 256
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        const unsigned long long mask = pass == 0 ? 0ull : (~0ull << (shift + 8));
+        for (int t = tid; t < nT; t += TK_THREADS) {
+            const unsigned long long k = order_key(row[t]);
+            if ((k & mask) == prefix) atomicAdd(&hist[(unsigned)(k >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int need = s_need;
+            int b = 255;
+            for (; b > 0; --b) {
+                if ((int)hist[b] >= need) break;
+                need -= (int)hist[b];
+            }
+            s_need = need;
+            s_prefix = prefix | ((unsigned long long)b << shift);
+        }
+        __syncthreads();
+    }
+    const unsigned long long kth = s_prefix;
+    const int need_eq = s_need;      // how many elements equal to kth belong to the top K
+    // count ties
+    if (tid == 0) { s_count = 0; s_run = 0; }
+    __syncthreads();
+    int my_eq = 0;
+    for (int t = tid; t < nT; t += TK_THREADS) my_eq += (order_key(row[t]) == kth);
+    my_eq = __reduce_add_sync(0xffffffffu, my_eq);
+    if ((tid & 31) == 0) atomicAdd(&s_run, my_eq);
+    __syncthreads();
+    if (tid == 0) { s_eq_skip = s_run - need_eq; s_run = 0; }   // ties to skip (lowest indices)
+    __syncthreads();
+    const int eq_skip = s_eq_skip;
+    // gather: everything above kth, and the ties with the largest indices
+    for (int base = 0; base < nT; base += TK_THREADS) {
+        const int t = base + tid;
+        unsigned long long k = 0ull;
+        bool gt = false, eq = false;
+        if (t < nT) { k = order_key(row[t]); gt = k > kth; eq = k == kth; }
+        bool take = gt;
+        if (eq_skip == 0) {
+            take = gt || eq;
+        } else {
+            // rank of this tie in index order
+            const unsigned bal = __ballot_sync(0xffffffffu, eq);
+            const int wrank = __popc(bal & ((1u << (tid & 31)) - 1u));
+            if ((tid & 31) == 0) warp_tot[tid >> 5] = __popc(bal);
+            __syncthreads();
+            int off = s_run;
+            for (int w = 0; w < (tid >> 5); ++w) off += warp_tot[w];
+            if (eq && off + wrank >= eq_skip) take = true;
+            __syncthreads();
+            if (tid == 0) {
+                int tot = 0;
+                for (int w = 0; w < TK_THREADS / 32; ++w) tot += warp_tot[w];
+                s_run += tot;
+            }
+            __syncthreads();
+        }
+        if (take) {
+            const int pos = atomicAdd(&s_count, 1);
+            if (pos < TK_MAXK) { skey[pos] = k; sidx[pos] = t; }
+        }
+    }
+    __syncthreads();
+    // pad to a power of two and bitonic-sort descending by (key, index)
+    int n2 = 1;
+    while (n2 < K) n2 <<= 1;
+    for (int i = K + tid; i < n2; i += TK_THREADS) { skey[i] = 0ull; sidx[i] = -1; }
+    __syncthreads();
+    for (int size = 2; size <= n2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = tid; i < n2; i += TK_THREADS) {
+                const int j = i ^ stride;
+                if (j > i) {
+                    const bool desc = (i & size) == 0;
+                    const unsigned long long ki = skey[i], kj = skey[j];
+                    const int ii = sidx[i], ij = sidx[j];
+                    const bool i_before_j = (ki > kj) || (ki == kj && ii > ij);
+                    if (i_before_j != desc) {
+                        skey[i] = kj; skey[j] = ki; sidx[i] = ij; sidx[j] = ii;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < K; i += TK_THREADS) {
+        const int t = sidx[i];
+        top_idx[(size_t)o * K + i] = t;
+        top_ev[(size_t)o * K + i] = t >= 0 ? row[t] : 0.0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// First seven columns of computeMetrics (delight/utils.py:213-227) from the final PDF; one warp
+// per target.  out [nO][8]: ztrue zmean std(zmean) zMAP std(zMAP) pdf(ztrue) cumpdf(ztrue) iMAP
+__global__ void metrics_kernel(int nO, int nz, const double* __restrict__ pdf, long long ld,
+                               const double* __restrict__ zgrid,
+                               const double* __restrict__ ztrue, double* __restrict__ out) {
+    const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (o >= nO) return;
+    const double* p = pdf + (size_t)o * ld;
+    double sw = 0, swz = 0, best = -INFINITY;
+    int ibest = 0x7fffffff;
+    for (int i = lane; i < nz; i += 32) {
+        const double w = p[i];
+        sw += w; swz += w * zgrid[i];
+        if (w > best) { best = w; ibest = i; }
+    }
+    sw = warp_sum(sw); swz = warp_sum(swz);
+    // argmax, first maximum (np.argmax)
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, s);
+        const int oi = __shfl_xor_sync(0xffffffffu, ibest, s);
+        if (ob > best || (ob == best && oi < ibest)) { best = ob; ibest = oi; }
+    }
+    const double zmean = swz / sw;
+    const double zmap = zgrid[ibest < nz ? ibest : 0];
+    double v1 = 0, v2 = 0;
+    for (int i = lane; i < nz; i += 32) {
+        const double w = p[i], d1 = zgrid[i] - zmean, d2 = zgrid[i] - zmap;
+        v1 += w * d1 * d1; v2 += w * d2 * d2;
+    }
+    v1 = warp_sum(v1); v2 = warp_sum(v2);
+    // np.interp(ztrue, grid, pdf) and np.interp(ztrue, grid, cumsum(pdf))
+    const double zt = ztrue ? ztrue[o] : -1.0;
+    double pz, cz;
+    int lo = 0;
+    if (zt <= zgrid[0]) lo = -1;
+    else if (zt >= zgrid[nz - 1]) lo = nz;
+    else {
+        int a = 0, b = nz - 1;               // grid[a] <= zt < grid[b]
+        while (b - a > 1) { const int mid = (a + b) >> 1; if (zgrid[mid] <= zt) a = mid; else b = mid; }
+        lo = a;
+    }
+    const int upto = lo < 0 ? 0 : (lo >= nz ? nz - 1 : lo);
+    double cs = 0;
+    for (int i = lane; i <= upto; i += 32) cs += p[i];
+    cs = warp_sum(cs);
+    if (lo < 0) { pz = p[0]; cz = p[0]; }
+    else if (lo >= nz) { pz = p[nz - 1]; cz = cs; }
+    else {
+        const double fr = (zt - zgrid[lo]) / (zgrid[lo + 1] - zgrid[lo]);
+        pz = (p[lo + 1] - p[lo]) * fr + p[lo];
+        cz = p[lo + 1] * fr + cs;
+    }
+    if (lane == 0) {
+        double* m = out + (size_t)o * 8;
+        m[0] = zt; m[1] = zmean; m[2] = sqrt(v1 / sw); m[3] = zmap; m[4] = sqrt(v2 / sw);
+        m[5] = pz; m[6] = cz; m[7] = (double)ibest;
+    }
+}
+
+// trapezoid weights of np.trapz(y, x=zgrid) written as a dot product (delight-apply.py:148):
+// w[0] = (z1-z0)/2, w[i] = (z[i+1]-z[i-1])/2, w[nz-1] = (z[nz-1]-z[nz-2])/2, 0 in the padding;
+// plus the z-dependent ell-prior terms of utils_cy.pyx:102-104,116 when ell_hat/ell_var vary.
+__global__ void zaux_kernel(int nz, int nzp, const double* __restrict__ zgrid,
+                            const double* __restrict__ eh, const double* __restrict__ ev,
+                            double* __restrict__ wz, double* __restrict__ zd) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nzp) return;
+    double w = 0.0;
+    if (i < nz) {
+        const double lo = zgrid[i > 0 ? i - 1 : 0];
+        const double hi = zgrid[i + 1 < nz ? i + 1 : nz - 1];
+        w = 0.5 * (hi - lo);
+    }
+    wz[i] = w;
+    if (eh != nullptr) {
+        const double h = i < nz ? eh[i] : 1.0, v = i < nz ? ev[i] : 1.0;
+        zd[i] = h / v; zd[nzp + i] = 1.0 / v; zd[2 * nzp + i] = h * h / v; zd[3 * nzp + i] = v;
+    }
+}
+
+// prior[t][z] = exp(-0.5 ((z - z_t) / sigma)^2)   (scripts/delight-apply.py:104), padded rows
+__global__ void zprior_kernel(int nT, int nz, int nzp, const double* __restrict__ zgrid,
+                              const double* __restrict__ ztrain, double sigma,
+                              double* __restrict__ prior) {
+    const int z = blockIdx.y * blockDim.x + threadIdx.x;
+    const int t = blockIdx.x;
+    if (z >= nzp) return;
+    double v = 0.0;
+    if (z < nz) {
+        const double d = (zgrid[z] - ztrain[t]) / sigma;
+        v = exp(-0.5 * d * d);
+    }
+    prior[(size_t)t * nzp + z] = v;
+}
+
+// legacy [nz][nT][nB] (scripts/delight-apply.py:84-85) -> device layout [nT][2nB][nzp]
+__global__ void relayout_grid_kernel(int nz, int nT, int nB, int nzp,
+                                     const double* __restrict__ mean,
+                                     const double* __restrict__ covar,
+                                     double* __restrict__ grid) {
+    // block = (32 z) x (all bands of one t), transposed through smem
+    extern __shared__ double tile[];     // [2][32][nB+1]
+    const int t = blockIdx.x;
+    const int zb = blockIdx.y * 32;
+    const int ld = nB + 1;
+    for (int i = threadIdx.x; i < 32 * nB; i += blockDim.x) {
+        const int zz = i / nB, b = i % nB;
+        const int z = zb + zz;
+        double a = 0.0, c = 1.0;
+        if (z < nz) {
+            a = mean[((size_t)z * nT + t) * nB + b];
+            c = covar[((size_t)z * nT + t) * nB + b];
+        }
+        tile[zz * ld + b] = a;
+        tile[32 * ld + zz * ld + b] = c;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * nB; i += blockDim.x) {
+        const int b = i / 32, zz = i % 32;
+        const int z = zb + zz;
+        if (z < nzp) {
+            grid[((size_t)t * 2 * nB + b) * nzp + z] = tile[zz * ld + b];
+            grid[((size_t)t * 2 * nB + nB + b) * nzp + z] = tile[32 * ld + zz * ld + b];
+        }
+    }
+}
+
+// explicit prior [nz][nT] (e.g. templateFitting.py:79-82) -> [nT][nzp]
+__global__ void relayout_prior_kernel(int nz, int nT, int nzp, const double* __restrict__ src,
+                                      double* __restrict__ dst) {
+    __shared__ double tile[32][33];
+    const int zb = blockIdx.x * 32, tb = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int z = zb + r, t = tb + tx;
+        tile[r][tx] = (z < nz && t < nT) ? src[(size_t)z * nT + t] : 0.0;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int t = tb + r, z = zb + tx;
+        if (t < nT && z < nzp) dst[(size_t)t * nzp + z] = tile[tx][r];
+    }
+}
+
+template <int NF, bool ZDEP>
+static int launch_fused_t(const FusedParams& p, cudaStream_t stream) {
+    constexpr int ROWS = 2 * NF + 1;
+    constexpr int TCS = tc_stride(NF);
+    const size_t smem = sizeof(double) * (FSTAGES * ROWS * FZC + FTPC * FZC + FTPC * TCS + FZC +
+                                          (ZDEP ? 4 * FZC : 0)) + 2 * FSTAGES * sizeof(uint64_t);
+    auto kern = fused_like_kernel<NF, ZDEP>;
+    DL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+    const int notile = (p.nO + FTPC - 1) / FTPC;
+    dim3 grid(p.nchunk * notile, p.nsplit);
+    if (dl_timing_enabled()) dl_timing_mark(stream, 0);
+    kern<<<grid, FTHREADS, smem, stream>>>(p);
+    if (dl_timing_enabled()) dl_timing_mark(stream, 1);
+    DL_CUDA_CHECK(cudaGetLastError());
+    dl_count_launch();
+    return DL_OK;
+}
+
+template <bool ZDEP>
+static int launch_fused_nf(int NF, const FusedParams& p, cudaStream_t stream) {
+    switch (NF) {
+        case 1: return launch_fused_t<1, ZDEP>(p, stream);
+        case 2: return launch_fused_t<2, ZDEP>(p, stream);
+        case 3: return launch_fused_t<3, ZDEP>(p, stream);
+        case 4: return launch_fused_t<4, ZDEP>(p, stream);
+        case 5: return launch_fused_t<5, ZDEP>(p, stream);
+        case 6: return launch_fused_t<6, ZDEP>(p, stream);
+        case 7: return launch_fused_t<7, ZDEP>(p, stream);
+        case 8: return launch_fused_t<8, ZDEP>(p, stream);
+    }
+    dl_set_error("fused likelihood supports 1..%d bands per target group, got %d", MAXNF, NF);
+    return DL_ERR_UNSUPPORTED;
+}
+
+}  // namespace dl
+
+using namespace dl;
+
+// ============================================================================ C ABI (device)
+extern "C" {
+
+int dl_fused_chunk() { return FZC; }
+int dl_fused_targets_per_cta() { return FTPC; }
+
+long long dl_fused_padded_nz(long long nz) { return (nz + FZC - 1) / FZC * FZC; }
+
+// bytes of scratch dl_like_fused_dev needs for (nO targets, nT training galaxies, nz, nsplit)
+long long dl_fused_workspace_bytes(long long nO, long long nT, long long nz, int nsplit,
+                                   int want_evid) {
+    const long long nzp = dl_fused_padded_nz(nz);
+    const long long nchunk = nzp / FZC;
+    auto al = [](long long x) { return (x + 255) & ~255ll; };
+    long long b = 0;
+    b += al((long long)tc_stride(MAXNF) * nO * 8);      // tconst
+    b += al((long long)nsplit * nO * nzp * 8);          // pdf_part
+    b += al(nchunk * nO * nT * 16);                     // evid_part
+    b += 2 * al((long long)nsplit * nchunk * nO * 8);   // Rw, Vw
+    b += 2 * al(nO * 8);                                // Rfin, invV
+    b += al(nzp * 8) + al(4 * nzp * 8);                 // wz, zdep
+    if (!want_evid) b += al(nO * nT * 8);               // evid (internal)
+    return b;
+}
+
+int dl_relayout_grid_dev(long long nz, long long nT, long long nB, const double* model_mean,
+                         const double* model_covar, double* grid, void* stream) {
+    DL_REQUIRE(nz > 0 && nT > 0 && nB > 0 && nB <= 64, "bad shape");
+    const int nzp = (int)dl_fused_padded_nz(nz);
+    dim3 g((unsigned)nT, (nzp + 31) / 32);
+    const size_t sm = sizeof(double) * 2 * 32 * (nB + 1);
+    relayout_grid_kernel<<<g, 256, sm, (cudaStream_t)stream>>>((int)nz, (int)nT, (int)nB, nzp,
+                                                               model_mean, model_covar, grid);
+    DL_CUDA_CHECK(cudaGetLastError());
+    dl_count_launch();
+    return DL_OK;
+}
+
+int dl_relayout_prior_dev(long long nz, long long nT, const double* prior_zt, double* prior_tz,
+                          void* stream) {
+    DL_REQUIRE(nz > 0 && nT > 0, "bad shape");
+    const int nzp = (int)dl_fused_padded_nz(nz);
+    dim3 g((nzp + 31) / 32, (unsigned)((nT + 31) / 32));
+    relayout_prior_kernel<<<g, 256, 0, (cudaStream_t)stream>>>((int)nz, (int)nT, nzp, prior_zt,
+                                                               prior_tz);
+    DL_CUDA_CHECK(cudaGetLastError());
+    dl_count_launch();
+    return DL_OK;
+}
+
+int dl_zprior_dev(long long nT, long long nz, const double* zgrid, const double* ztrain,
+                  double sigma, double* prior_tz, void* stream) {
+    DL_REQUIRE(nz > 0 && nT > 0 && sigma > 0, "bad shape");
+    const int nzp = (int)dl_fused_padded_nz(nz);
+    dim3 g((unsigned)nT, (nzp + 127) / 128);
+    zprior_kernel<<<g, 128, 0, (cudaStream_t)stream>>>((int)nT, (int)nz, nzp, zgrid, ztrain,
+                                                       sigma, prior_tz);
+    DL_CUDA_CHECK(cudaGetLastError());
+    dl_count_launch();
+    return DL_OK;
+}
+
+// Fused likelihood + apply epilogue for one group of targets sharing the same band list.
+//   obs, var     [nO][nf]   target fluxes / variances restricted to `bands`
+//   bands        [nf]       HOST array of band indices into the grid (0 <= b < nB)
+//   grid         [nT][2nB][nzp] device, prior [nT][nzp] device (nzp = dl_fused_padded_nz(nz))
+//   zgrid        [nz] device
+//   ell_hat/ell_var: scalars, or (ell_hat_z, ell_var_z != NULL) device vectors [nz]
+//   outputs (device): pdf [nO][ld_pdf]; evid [nO][nT] or NULL; top_idx [nO][K] int64,
+//                     top_ev [nO][K] (K may be 0)
+int dl_like_fused_dev(long long nO, long long nT, long long nz, long long nB, int nf,
+                      const int* bands, const double* obs, const double* var,
+                      const double* grid, const double* prior, const double* zgrid,
+                      double ell_hat, double ell_var, const double* ell_hat_z,
+                      const double* ell_var_z, int nsplit, int K, double* pdf, long long ld_pdf,
+                      double* evid, long long* top_idx, double* top_ev, void* workspace,
+                      long long workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DL_REQUIRE(nO > 0 && nT > 0 && nz > 1 && nB > 0, "bad shape");
+    DL_REQUIRE(nf >= 1 && nf <= MAXNF, "1..8 bands per target group");
+    DL_REQUIRE(nsplit >= 1 && nsplit <= nT, "bad nsplit");
+    DL_REQUIRE(K >= 0 && K <= TK_MAXK && K <= nT, "0 <= K <= min(nT, 1024)");
+    DL_REQUIRE(ld_pdf >= nz, "ld_pdf < nz");
+    const bool zdep = ell_hat_z != nullptr && ell_var_z != nullptr;
+    const long long need = dl_fused_workspace_bytes(nO, nT, nz, nsplit, evid != nullptr || K == 0);
+    DL_REQUIRE(workspace && workspace_bytes >= need, "workspace too small");
+    const int nzp = (int)dl_fused_padded_nz(nz);
+    const int nchunk = nzp / FZC;
+
+    char* w = (char*)workspace;
+    auto take = [&](size_t bytes) { char* r = w; w += (bytes + 255) & ~(size_t)255; return r; };
+    double* tconst = (double*)take((size_t)tc_stride(MAXNF) * nO * 8);
+    double* pdf_part = (double*)take((size_t)nsplit * nO * nzp * 8);
+    double2* evid_part = (double2*)take((size_t)nchunk * nO * nT * 16);
+    double* Rw = (double*)take((size_t)nsplit * nchunk * nO * 8);
+    double* Vw = (double*)take((size_t)nsplit * nchunk * nO * 8);
+    double* Rfin = (double*)take((size_t)nO * 8);
+    double* invV = (double*)take((size_t)nO * 8);
+    double* wz = (double*)take((size_t)nzp * 8);
+    double* zd = (double*)take((size_t)4 * nzp * 8);
+    double* evid_int = evid ? evid : (K > 0 ? (double*)take((size_t)nO * nT * 8) : nullptr);
+    DL_REQUIRE((size_t)(w - (char*)workspace) <= (size_t)workspace_bytes, "workspace accounting");
+
+    zaux_kernel<<<(unsigned)((nzp + 127) / 128), 128, 0, stream>>>(
+        (int)nz, nzp, zgrid, zdep ? ell_hat_z : nullptr, zdep ? ell_var_z : nullptr, wz, zd);
+    DL_CUDA_CHECK(cudaGetLastError());
+    dl_count_launch();
+
+    prep_targets_kernel<<<(unsigned)((nO + 127) / 128), 128, 0, stream>>>(
+        (int)nO, nf, obs, var, zdep ? 1.0 : ell_hat, zdep ? 1.0 : ell_var, tconst);
+    DL_CUDA_CHECK(cudaGetLastError());
+    dl_count_launch();
+
+    FusedParams p;
+    p.grid = grid; p.prior = prior; p.tconst = tconst; p.wz = wz; p.zdep = zd;
+    p.pdf_part = pdf_part; p.evid_part = evid_part; p.Rw = Rw; p.Vw = Vw;
+    for (int f = 0; f < MAXNF; ++f) {
+        p.bands[f] = f < nf ? bands[f] : 0;
+        DL_REQUIRE(p.bands[f] >= 0 && p.bands[f] < nB, "band index out of range");
+    }
+    p.nB = (int)nB; p.nz = (int)nz; p.nzp = nzp; p.nT = (int)nT; p.nO = (int)nO;
+    p.nchunk = nchunk; p.nsplit = nsplit;
+    int rc = zdep ? launch_fused_nf<true>(nf, p, stream) : launch_fused_nf<false>(nf, p, stream);
+    if (rc != DL_OK) return rc;
+
+    finalize_scales_kernel<<<(unsigned)((nO + 127) / 128), 128, 0, stream>>>(
+        (int)nO, nsplit * nchunk, Rw, Vw, Rfin, invV);
+    DL_CUDA_CHECK(cudaGetLastError());
+    dl_count_launch();
+    {
+        dim3 g((unsigned)nO, (unsigned)((nz + 127) / 128));
+        finalize_pdf_kernel<<<g, 128, 0, stream>>>((int)nO, (int)nz, nzp, nchunk, nsplit,
+                                                   pdf_part, Rw, Rfin, invV, pdf, ld_pdf);
+        DL_CUDA_CHECK(cudaGetLastError());
+        dl_count_launch();
+    }
+    if (evid_int) {
+        dim3 g((unsigned)nO, (unsigned)((nT + 127) / 128));
+        finalize_evid_kernel<<<g, 128, 0, stream>>>((int)nO, (int)nT, nchunk, evid_part, Rfin,
+                                                    invV, evid_int);
+        DL_CUDA_CHECK(cudaGetLastError());
+        dl_count_launch();
+    }
+    if (K > 0) {
+        DL_REQUIRE(top_idx && top_ev, "top-K outputs missing");
+        topk_kernel<<<(unsigned)nO, TK_THREADS, 0, stream>>>((int)nT, K, evid_int, top_idx,
+                                                            top_ev);
+        DL_CUDA_CHECK(cudaGetLastError());
+        dl_count_launch();
+    }
+    return DL_OK;
+}
+
+int dl_metrics_dev(long long nO, long long nz, const double* pdf, long long ld_pdf,
+                   const double* zgrid, const double* ztrue, double* out, void* stream) {
+    DL_REQUIRE(nO > 0 && nz > 1 && ld_pdf >= nz, "bad shape");
+    metrics_kernel<<<(unsigned)((nO + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+        (int)nO, (int)nz, pdf, ld_pdf, zgrid, ztrue, out);
+    DL_CUDA_CHECK(cudaGetLastError());
+    dl_count_launch();
+    return DL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+"""Drop-in for the reference's Cython module `delight.utils_cy` (hot-path operators only).
+
+Same function names, positional/keyword parameter names, array layouts and in-place output
+contract as delight/utils_cy.pyx; the arithmetic runs in CUDA (libdelight_b200.so).  Inputs are
+NumPy arrays (any strides); like the Cython typed-memoryview coercion, a wrong dtype or rank
+raises ValueError before anything is computed.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+__all__ = ["approx_flux_likelihood_cy", "find_positions", "kernel_parts_interp"]
+
+
+def _view(a, dtype, ndim, name):
+    if not isinstance(a, np.ndarray):
+        a = np.asarray(a)
+    if a.dtype != dtype:
+        raise ValueError("Buffer dtype mismatch for %s, expected '%s' but got '%s'"
+                         % (name, np.dtype(dtype).name, a.dtype.name))
+    if a.ndim != ndim:
+        raise ValueError("Buffer has wrong number of dimensions for %s (expected %d, got %d)"
+                         % (name, ndim, a.ndim))
+    return a
+
+
+def _dev(a):
+    torch = _lib.require_cuda()
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def approx_flux_likelihood_cy(like, nz, nt, nf, f_obs, f_obs_var, f_mod, f_mod_covar,
+                              ell_hat, ell_var):
+    """delight/utils_cy.pyx:83-128.  Fills like[nz, nt] in place with exp(L - max L)."""
+    like = _view(like, np.float64, 2, "like")
+    f_obs = _view(f_obs, np.float64, 1, "f_obs")
+    f_obs_var = _view(f_obs_var, np.float64, 1, "f_obs_var")
+    f_mod = _view(f_mod, np.float64, 3, "f_mod")
+    f_mod_covar = _view(f_mod_covar, np.float64, 3, "f_mod_covar")
+    ell_hat = _view(ell_hat, np.float64, 1, "ell_hat")
+    ell_var = _view(ell_var, np.float64, 1, "ell_var")
+    nz, nt, nf = int(nz), int(nt), int(nf)
+    if nz * nt == 0:
+        return
+    if like.shape[0] < nz or like.shape[1] < nt or f_mod.shape[0] < nz or f_mod.shape[1] < nt \
+            or f_mod.shape[2] < nf or f_mod_covar.shape[:2] != f_mod.shape[:2] \
+            or f_mod_covar.shape[2] < nf or f_obs.size < nf or f_obs_var.size < nf \
+            or ell_hat.size < nz or ell_var.size < nz:
+        raise ValueError("array shapes are inconsistent with nz=%d nt=%d nf=%d" % (nz, nt, nf))
+    torch = _lib.require_cuda()
+    d_mod = _dev(f_mod[:nz, :nt, :nf])
+    d_cov = _dev(f_mod_covar[:nz, :nt, :nf])
+    d_obs, d_var = _dev(f_obs[:nf]), _dev(f_obs_var[:nf])
+    d_eh, d_ev = _dev(ell_hat[:nz]), _dev(ell_var[:nz])
+    d_like = torch.empty((nz, nt), dtype=torch.float64, device="cuda")
+    scratch = torch.empty(1, dtype=torch.int64, device="cuda")
+    _lib.check(_lib.lib().dl_approx_flux_likelihood_dev(
+        _lib.ptr(d_like), nz, nt, nf, _lib.ptr(d_obs), _lib.ptr(d_var), _lib.ptr(d_mod),
+        _lib.ptr(d_cov), _lib.ptr(d_eh), _lib.ptr(d_ev), _lib.ptr(scratch), _lib.stream_ptr()))
+    like[:nz, :nt] = d_like.cpu().numpy()
+
+
+def find_positions(NO1, nz, fz1, p1s, fzGrid):
+    """delight/utils_cy.pyx:10-22.  p1s[o] = first bin with fzGrid[p] <= fz1[o] <= fzGrid[p+1];
+    entries whose value lies outside the grid are left untouched."""
+    fz1 = _view(fz1, np.float64, 1, "fz1")
+    p1s = _view(p1s, np.int64, 1, "p1s")
+    fzGrid = _view(fzGrid, np.float64, 1, "fzGrid")
+    NO1, nz = int(NO1), int(nz)
+    if NO1 == 0 or nz < 2:
+        return
+    if fz1.size < NO1 or p1s.size < NO1 or fzGrid.size < nz:
+        raise ValueError("array shapes are inconsistent with NO1=%d nz=%d" % (NO1, nz))
+    d_f, d_p, d_g = _dev(fz1[:NO1]), _dev(p1s[:NO1]), _dev(fzGrid[:nz])
+    _lib.check(_lib.lib().dl_find_positions_dev(NO1, nz, _lib.ptr(d_f), _lib.ptr(d_p),
+                                               _lib.ptr(d_g), _lib.stream_ptr()))
+    p1s[:NO1] = d_p.cpu().numpy()
+
+
+def kernel_parts_interp(NO1, NO2, Kinterp, b1, fz1, p1s, b2, fz2, p2s, fzGrid, Kgrid):
+    """delight/utils_cy.pyx:53-79 (identical twin of photoz_kernels_cy.pyx:9-35)."""
+    from .photoz_kernels_cy import kernel_parts_interp as _kpi
+    return _kpi(NO1, NO2, Kinterp, b1, fz1, p1s, b2, fz2, p2s, fzGrid, Kgrid)

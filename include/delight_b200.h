@@ -1,0 +1,168 @@
+/*
+ * delight_b200 -- C ABI of the B200-native photo-z inference hot path of ixkael/Delight.
+ *
+ * libdelight_b200.so exports exactly these symbols.  Conventions
+ *   - every function returns 0 (DL_OK) or a DL_ERR_* code; dl_last_error() gives the message
+ *     (thread local).  The reference's Cython operators have no error channel at all
+ *     (boundscheck=False, photoz_kernels_cy.pyx:1); shape checks that Cython's memoryview
+ *     coercion performs (ValueError) are done by the Python shim modules.
+ *   - all floating point data is IEEE double, all indices are 64-bit signed (Cython `long`).
+ *   - `_host` entry points take HOST pointers and do their own transfers (these are what an FFI
+ *     binding of the reference operators binds);  `_dev` entry points take DEVICE pointers and a
+ *     cudaStream_t passed as void* (NULL = default stream) and never synchronise.
+ *   - arrays are C-contiguous unless a leading dimension `ld` (in elements) is given.
+ *
+ * References are to files under the reference repository root.
+ */
+#ifndef DELIGHT_B200_H
+#define DELIGHT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DL_OK 0
+#define DL_ERR_INVALID 1
+#define DL_ERR_CUDA 2
+#define DL_ERR_NOMEM 3
+#define DL_ERR_UNSUPPORTED 4
+
+const char* dl_last_error(void);
+int dl_version(void);
+int dl_device_info(int* sm_count, int* cc_major, int* cc_minor, long long* global_mem);
+
+/* ------------------------------------------------------------------------------------------
+ * (1) approx_flux_likelihood_cy          replaces delight/utils_cy.pyx:83-128
+ *     like [nz][nt] (out), f_obs/f_obs_var [nf], f_mod/f_mod_covar [nz][nt][nf],
+ *     ell_hat/ell_var [nz].  Result = exp(L - max L) over the whole call, as the reference.
+ * ---------------------------------------------------------------------------------------- */
+int dl_approx_flux_likelihood_host(double* like, long long nz, long long nt, long long nf,
+                                   const double* f_obs, const double* f_obs_var,
+                                   const double* f_mod, const double* f_mod_covar,
+                                   const double* ell_hat, const double* ell_var);
+int dl_approx_flux_likelihood_dev(double* like, long long nz, long long nt, long long nf,
+                                  const double* f_obs, const double* f_obs_var,
+                                  const double* f_mod, const double* f_mod_covar,
+                                  const double* ell_hat, const double* ell_var,
+                                  void* scratch8, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (2) kernelparts                        replaces delight/photoz_kernels_cy.pyx:103-177
+ *     Outputs [NO1][NO2] are ACCUMULATED into and then divided by norms[b1]*norms[b2]
+ *     (pyx:149-177); gradients are only touched when grad_needed.  Output order KL, KC as in
+ *     the reference signature.  lines_sig of the reference signature is unused there (never
+ *     read) and is not part of this ABI.  0 <= NL <= 8.
+ * ---------------------------------------------------------------------------------------- */
+int dl_kernelparts_host(long long NO1, long long NO2, long long NC, long long NL, double alpha_C,
+                        double alpha_L, long long nB, const double* fcoefs_amp,
+                        const double* fcoefs_mu, const double* fcoefs_sig,
+                        const double* lines_mu, const double* norms, const long long* b1,
+                        const double* fz1, const long long* b2, const double* fz2,
+                        int grad_needed, double* KL, double* KC, double* D_alpha_C,
+                        double* D_alpha_L, double* D_alpha_z);
+int dl_kernelparts_dev(long long NO1, long long NO2, long long NC, long long NL, double alpha_C,
+                       double alpha_L, const double* fcoefs_amp, const double* fcoefs_mu,
+                       const double* fcoefs_sig, const double* lines_mu, const double* norms,
+                       const long long* b1, const double* fz1, const long long* b2,
+                       const double* fz2, int grad_needed, double* KL, double* KC,
+                       double* D_alpha_C, double* D_alpha_L, double* D_alpha_z, long long ld,
+                       void* stream);
+
+/* (3) kernelparts_diag                   replaces delight/photoz_kernels_cy.pyx:38-100
+ *     KL/KC [NO1] overwritten, D_alpha_C/D_alpha_L accumulated then normalised. */
+int dl_kernelparts_diag_host(long long NO1, long long NC, long long NL, double alpha_C,
+                             double alpha_L, long long nB, const double* fcoefs_amp,
+                             const double* fcoefs_mu, const double* fcoefs_sig,
+                             const double* lines_mu, const double* norms, const long long* b1,
+                             const double* fz1, int grad_needed, double* KL, double* KC,
+                             double* D_alpha_C, double* D_alpha_L);
+int dl_kernelparts_diag_dev(long long NO1, long long NC, long long NL, double alpha_C,
+                            double alpha_L, const double* fcoefs_amp, const double* fcoefs_mu,
+                            const double* fcoefs_sig, const double* lines_mu,
+                            const double* norms, const long long* b1, const double* fz1,
+                            int grad_needed, double* KL, double* KC, double* D_alpha_C,
+                            double* D_alpha_L, void* stream);
+
+/* (4) find_positions                     replaces delight/utils_cy.pyx:10-22
+ *     p1s[o] = first p with fzGrid[p] <= fz1[o] <= fzGrid[p+1]; untouched when outside. */
+int dl_find_positions_host(long long NO1, long long nz, const double* fz1, long long* p1s,
+                           const double* fzGrid);
+int dl_find_positions_dev(long long NO1, long long nz, const double* fz1, long long* p1s,
+                          const double* fzGrid, void* stream);
+
+/* (5) kernel_parts_interp                replaces delight/photoz_kernels_cy.pyx:9-35
+ *     Kgrid [nB][nB][nzg][nzg], Kinterp [NO1][NO2] overwritten. */
+int dl_kernel_parts_interp_host(long long NO1, long long NO2, double* Kinterp,
+                                const long long* b1, const double* fz1, const long long* p1s,
+                                const long long* b2, const double* fz2, const long long* p2s,
+                                const double* fzGrid, const double* Kgrid, long long nB,
+                                long long nzg);
+int dl_kernel_parts_interp_dev(long long NO1, long long NO2, double* Kinterp, long long ld,
+                               const long long* b1, const double* fz1, const long long* p1s,
+                               const long long* b2, const double* fz2, const long long* p2s,
+                               const double* fzGrid, const double* Kgrid, long long nB,
+                               long long nzg, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Batched / fused entry points used by the new host path (device pointers only).
+ * ---------------------------------------------------------------------------------------- */
+
+/* Photoz_kernel.construct_interpolators  replaces delight/photoz_kernels.py:342-416
+ * (nB^2 kernelparts calls + nB kernelparts_diag calls) by one launch.
+ * KC_grid/KL_grid [nB][nB][nzg][nzg], KC_diag/KL_diag [nB][nzg], fzGrid = 1 + redshiftGridGP. */
+int dl_kernel_grids_dev(long long nB, long long nzg, long long NC, long long NL, double alpha_C,
+                        double alpha_L, const double* fcoefs_amp, const double* fcoefs_mu,
+                        const double* fcoefs_sig, const double* lines_mu, const double* norms,
+                        const double* fzGrid, double* KC_grid, double* KL_grid, double* KC_diag,
+                        double* KL_diag, void* stream);
+
+/* Model-grid layout of the fused likelihood: [nT][2*nB][nzp], rows 0..nB-1 = band means,
+ * nB..2nB-1 = band variances, z contiguous, nzp = dl_fused_padded_nz(nz) (padding: mean 0,
+ * variance 1).  Priors are [nT][nzp] (padding 0). */
+int dl_fused_chunk(void);
+int dl_fused_targets_per_cta(void);
+long long dl_fused_padded_nz(long long nz);
+long long dl_fused_workspace_bytes(long long nO, long long nT, long long nz, int nsplit,
+                                   int evid_is_output_or_unused);
+
+/* legacy [nz][nT][nB] arrays of scripts/delight-apply.py:84-85 -> fused layout */
+int dl_relayout_grid_dev(long long nz, long long nT, long long nB, const double* model_mean,
+                         const double* model_covar, double* grid, void* stream);
+/* explicit prior [nz][nT] (e.g. scripts/templateFitting.py:79-82) -> [nT][nzp] */
+int dl_relayout_prior_dev(long long nz, long long nT, const double* prior_zt, double* prior_tz,
+                          void* stream);
+/* Gaussian redshift prior of scripts/delight-apply.py:104 -> [nT][nzp] */
+int dl_zprior_dev(long long nT, long long nz, const double* zgrid, const double* ztrain,
+                  double sigma, double* prior_tz, void* stream);
+
+/* Fused likelihood + apply epilogue   replaces scripts/delight-apply.py:137-162 x nO targets
+ * (approx_flux_likelihood_cy, like*=prior, pdf=sum_t, evid=trapz_z, top-K) for one group of
+ * targets that share the band list `bands` (HOST array, nf <= 8 entries).
+ *   obs/var [nO][nf]; ell_hat/ell_var scalars, or device vectors ell_hat_z/ell_var_z [nz]
+ *   pdf [nO][ld_pdf] out; evid [nO][nT] out or NULL; top_idx [nO][K] / top_ev [nO][K] out
+ *   (K = 0: skipped).  Ties: descending evidence, equal -> larger index first. */
+int dl_like_fused_dev(long long nO, long long nT, long long nz, long long nB, int nf,
+                      const int* bands, const double* obs, const double* var,
+                      const double* grid, const double* prior, const double* zgrid,
+                      double ell_hat, double ell_var, const double* ell_hat_z,
+                      const double* ell_var_z, int nsplit, int K, double* pdf, long long ld_pdf,
+                      double* evid, long long* top_idx, double* top_ev, void* workspace,
+                      long long workspace_bytes, void* stream);
+
+/* computeMetrics core                  replaces delight/utils.py:213-227 (first 7 columns)
+ * out [nO][8]: ztrue zmean std(zmean) zMAP std(zMAP) pdf(ztrue) cumpdf(ztrue) argmax-index */
+int dl_metrics_dev(long long nO, long long nz, const double* pdf, long long ld_pdf,
+                   const double* zgrid, const double* ztrue, double* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Measurement hooks (used by bench.py; no effect on results)
+ * ---------------------------------------------------------------------------------------- */
+long long dl_launch_count(void);                 /* kernels launched by this library so far */
+int dl_timing_enable(int on);                    /* CUDA-event timing of the fused kernel */
+int dl_timing_collect(double* total_ms, int* launches);
+int dl_fp64_peak(int reps, double* tflops);      /* measured FP64 FMA peak of the device */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DELIGHT_B200_H */

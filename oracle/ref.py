@@ -57,8 +57,14 @@ def _install_shims():
                 __mul__ = __rmul__ = __add__ = __radd__ = __sub__ = __rsub__ = _arith
                 __truediv__ = __rtruediv__ = _arith
 
+            def _module_getattr(name):
+                if name.startswith("__"):
+                    raise AttributeError(name)
+                return _Anything()
+
             plt.subplots = lambda *a, **k: (_Anything(), _Anything())
-            plt.__getattr__ = lambda name: _Anything()
+            plt.__getattr__ = _module_getattr
+            plt.__file__ = mpl.__file__ = "<delight oracle stub>"
             mpl.pyplot = plt
             mpl.use = lambda *a, **k: None
             sys.modules["matplotlib"] = mpl

@@ -1,0 +1,96 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol of include/delight_b200.h,
+host-side logic (band grouping, rank partition, argument validation), no compute calls."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import delight_b200
+from delight_b200 import _lib, apply, utils_cy, photoz_kernels_cy
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    txt = open(os.path.join(REPO, "include", "delight_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(dl_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    names = _header_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), "libdelight_b200.so does not export %s" % n
+    assert sorted(_lib.EXPORTED) == names
+    assert L.dl_version() >= 100
+
+
+def test_padding_and_workspace_queries():
+    L = _lib.lib()
+    c = L.dl_fused_chunk()
+    assert c == 128 and L.dl_fused_targets_per_cta() == 32
+    assert L.dl_fused_padded_nz(1500) == 1536 and L.dl_fused_padded_nz(128) == 128
+    a = L.dl_fused_workspace_bytes(32, 1000, 1500, 1, 0)
+    b = L.dl_fused_workspace_bytes(64, 1000, 1500, 1, 0)
+    assert 0 < a < b
+
+
+def test_rank_partition_matches_reference_formula():
+    # scripts/delight-apply.py:50-53
+    for n in (0, 1, 7, 1000, 12345):
+        for size in (1, 2, 3, 8):
+            spans = [apply.partition(n, r, size) for r in range(size)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+                assert a1 == b0
+            for r, (f, l) in enumerate(spans):
+                assert f == int(r * n / float(size))
+                assert l == int(min(n, (r + 1) * n / float(size)))
+
+
+def test_target_grouping_by_band_set():
+    fl = np.arange(20.0).reshape(4, 5) + 1
+    bands = np.array([[0, 1, 2, 3, 4], [0, 1, 3, 4, -1], [0, 1, 2, 3, 4], [1, 2, -1, -1, -1]])
+    nf = np.array([5, 4, 5, 2])
+    t = apply.Targets(fl, fl, bands, nf)
+    groups = {b: list(i) for b, i in t.groups()}
+    assert groups == {(0, 1, 2, 3, 4): [0, 2], (0, 1, 3, 4): [1], (1, 2): [3]}
+    with pytest.raises(ValueError):
+        apply.Targets(fl, fl, bands, np.array([5, 4, 5, 0]))
+
+
+def test_dropin_signatures_and_dtype_errors():
+    import inspect
+    sig = inspect.signature(utils_cy.approx_flux_likelihood_cy)
+    assert list(sig.parameters) == ["like", "nz", "nt", "nf", "f_obs", "f_obs_var", "f_mod",
+                                    "f_mod_covar", "ell_hat", "ell_var"]
+    sig = inspect.signature(photoz_kernels_cy.kernelparts)
+    assert list(sig.parameters)[-5:] == ["KL", "KC", "D_alpha_C", "D_alpha_L", "D_alpha_z"]
+    like = np.zeros((3, 2), dtype=np.float32)
+    with pytest.raises(ValueError, match="dtype mismatch"):
+        utils_cy.approx_flux_likelihood_cy(like, 3, 2, 1, np.ones(1), np.ones(1),
+                                           np.ones((3, 2, 1)), np.ones((3, 2, 1)), np.ones(3),
+                                           np.ones(3))
+    with pytest.raises(ValueError, match="dimensions"):
+        utils_cy.find_positions(2, 3, np.ones((2, 1)), np.zeros(2, dtype=np.int64), np.ones(3))
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(_lib.DelightB200Error):
+        utils_cy.find_positions(2, 3, np.array([0.5, 1.5]), np.zeros(2, dtype=np.int64),
+                                np.array([0., 1., 2.]))
+
+
+def test_product_never_references_the_oracle():
+    pkg = os.path.join(REPO, "delight_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(root, f)).read()
+                assert "oracle" not in txt, os.path.join(root, f)
