@@ -93,7 +93,9 @@ __device__ __forceinline__ double exp_nonpos(double x) {
     // scale by 2^n through the exponent bits; results below 2^-1021 flush to zero
     int hi = __double2hiint(p) + (n << 20);
     double res = __hiloint2double(hi, __double2loint(p));
-    return (x >= -708.0) ? res : ((x != x) ? x : 0.0);
+    // x >= -708 is false for NaN: return the NaN itself then (detected on the exponent bits by
+    // the integer pipe), 0 for underflow / -inf
+    return (x >= -708.0) ? res : ((__double2hiint(x) & 0x7fffffff) > 0x7ff00000 ? x : 0.0);
 }
 
 __device__ __forceinline__ double warp_max(double v) {

@@ -156,66 +156,113 @@ __global__ void __launch_bounds__(FTHREADS, 2) fused_like_kernel(const FusedPara
             }
             const double pr = st[2 * NF * FZC + zl];
             const double wzv = wz_sm[zl];
-            const bool valid = (z0 + zl) < p.nz;
+            // padded redshifts get x = -inf: they never move R or V and contribute exactly 0
+            const double xmask = ((z0 + zl) < p.nz) ? 0.0 : -INFINITY;
             double zot = 0, ztt = 0, zoo = 0, zev = 1.0;
             if (ZDEP) {
                 zot = zd_sm[zl]; ztt = zd_sm[FZC + zl]; zoo = zd_sm[2 * FZC + zl];
                 zev = zd_sm[3 * FZC + zl];
             }
+            // ---- phase A: branch-free; written as three sweeps over the warp's FTO targets so
+            //      that each sweep offers FTO (or FTO x NF) independent dependency chains to the
+            //      FP64 pipe (the kernel is latency-bound otherwise: 4 warps per scheduler).
+            double x[FTO], y[FTO], sarg[FTO];
+            double e2[FTO];
+            // A1 -- pass 0: observed variances only (utils_cy.pyx:101-113 with ellML = 0)
 #pragma unroll
             for (int o = 0; o < FTO; ++o) {
                 const double* tc = tcw + o * TCS;
-                const double hc = tc[5 * NF + 0];
-                const double ic = tc[5 * NF + 1];
-                double pOT, pTT, pOO;
+                double fot, ftt;
                 if (ZDEP) {
                     const double c = tc[5 * NF + 5];
-                    pOT = c * zot; pTT = c * ztt; pOO = c * zoo;
+                    fot = c * zot; ftt = c * ztt;
                 } else {
-                    pOT = tc[5 * NF + 2]; pTT = tc[5 * NF + 3]; pOO = tc[5 * NF + 4];
+                    fot = tc[5 * NF + 2]; ftt = tc[5 * NF + 3];
                 }
-                // pass 0: observed variances only (utils_cy.pyx:101-113 with ellML = 0)
-                double fot = pOT, ftt = pTT;
 #pragma unroll
                 for (int f = 0; f < NF; ++f) {
                     fot = fma(m[f], tc[f], fot);
                     ftt = fma(m2[f], tc[NF + f], ftt);
                 }
                 const double ell = fot * rcp_fast(ftt);
-                const double e2 = ell * (ell * ic);
-                // pass 1: variance inflated by ell^2 * model variance (utils_cy.pyx:107-112)
-                fot = pOT; ftt = pTT;
-                double foo = pOO, P = zev;
+                e2[o] = ell * (ell * tc[5 * NF + 1]);
+            }
+            // A2 -- pass 1: variance inflated by ell^2 * model variance (utils_cy.pyx:107-112)
+            double sot[FTO], stt[FTO], soo[FTO], P[FTO];
+#pragma unroll
+            for (int o = 0; o < FTO; ++o) {
+                const double* tc = tcw + o * TCS;
+                double fot, ftt, foo;
+                if (ZDEP) {
+                    const double c = tc[5 * NF + 5];
+                    fot = c * zot; ftt = c * ztt; foo = c * zoo;
+                } else {
+                    fot = tc[5 * NF + 2]; ftt = tc[5 * NF + 3]; foo = tc[5 * NF + 4];
+                }
+                double pp = zev;
 #pragma unroll
                 for (int f = 0; f < NF; ++f) {
-                    const double var = fma(e2, cv[f], tc[2 * NF + f]);
+                    const double var = fma(e2[o], cv[f], tc[2 * NF + f]);
                     const double r = rcp_fast(var);
                     const double tm = m[f] * r;
                     fot = fma(tm, tc[3 * NF + f], fot);
                     ftt = fma(tm, m[f], ftt);
                     foo = fma(tc[4 * NF + f], r, foo);
-                    P *= var;
+                    pp *= var;
                 }
-                const double y = rsqrt_fast(P * ftt);       // (det)^-1/2   (:111-117)
-                const double rF = (y * y) * P;              // 1 / FTT
-                const double chi2 = fma(-(fot * rF), fot, foo);  // :115
-                double x = hc * chi2;
-                x = valid ? x : -INFINITY;
-                double sarg = x - R[o];
-                if (__any_sync(0xffffffffu, sarg > 0.0)) {
-                    // rare: the warp met a better cell than its reference exponent
-                    const double xm = warp_max(x);
-                    const double fs = exp(R[o] - xm);
-                    R[o] = xm; V[o] *= fs; E[o] *= fs;
+                sot[o] = fot; stt[o] = ftt; soo[o] = foo; P[o] = pp;
+            }
+            // A3 -- chi2 and (det)^-1/2 (utils_cy.pyx:111-118)
 #pragma unroll
-                    for (int zj = 0; zj < FZT; ++zj) pdfw[o * FZC + zj * 32 + lane] *= fs;
-                    sarg = x - xm;
+            for (int o = 0; o < FTO; ++o) {
+                const double hc = tcw[o * TCS + 5 * NF + 0];
+                y[o] = rsqrt_fast(P[o] * stt[o]);
+                const double rF = (y[o] * y[o]) * P[o];      // 1 / FTT
+                const double chi2 = fma(-(sot[o] * rF), sot[o], soo[o]);
+                x[o] = fma(hc, chi2, xmask);                 // -chi2/2 in the target's units
+                sarg[o] = x[o] - R[o];
+            }
+            // ---- phase B: rare -- the warp met a better cell than a reference exponent
+            {
+                bool up = false;
+#pragma unroll
+                for (int o = 0; o < FTO; ++o) up |= __double2hiint(sarg[o]) > 0;
+                if (__any_sync(0xffffffffu, up)) {
+#pragma unroll
+                    for (int o = 0; o < FTO; ++o) {
+                        if (__any_sync(0xffffffffu, sarg[o] > 0.0)) {
+                            const double xm = warp_max(x[o]);
+                            const double fs = exp(R[o] - xm);
+                            R[o] = xm; V[o] *= fs; E[o] *= fs;
+#pragma unroll
+                            for (int zj = 0; zj < FZT; ++zj) pdfw[o * FZC + zj * 32 + lane] *= fs;
+                            sarg[o] = x[o] - xm;
+                        }
+                    }
                 }
-                const double v = exp_nonpos(sarg) * y;       // :118,128 up to the global scale
-                if (__any_sync(0xffffffffu, v > V[o])) V[o] = fmax(V[o], warp_max(v));
-                const double vp = v * pr;                    // delight-apply.py:145
-                pdfw[o * FZC + zl] += vp;                    // :147
-                E[o] = fma(vp, wzv, E[o]);                   // :148
+            }
+            // ---- phase C: exp, FTO independent chains                 (:118,128 up to scale)
+            double v[FTO];
+#pragma unroll
+            for (int o = 0; o < FTO; ++o) v[o] = exp_nonpos(sarg[o]) * y[o];
+            // ---- phase D: running max of the un-priored value (both operands are >= 0, so the
+            //      comparison is done on the bit patterns by the integer pipe)
+            {
+                bool up = false;
+#pragma unroll
+                for (int o = 0; o < FTO; ++o)
+                    up |= __double_as_longlong(v[o]) > __double_as_longlong(V[o]);
+                if (__any_sync(0xffffffffu, up)) {
+#pragma unroll
+                    for (int o = 0; o < FTO; ++o) V[o] = fmax(V[o], warp_max(v[o]));
+                }
+            }
+            // ---- phase E: prior, PDF and evidence accumulation  (delight-apply.py:145-148)
+#pragma unroll
+            for (int o = 0; o < FTO; ++o) {
+                const double vp = v[o] * pr;
+                pdfw[o * FZC + zl] += vp;
+                E[o] = fma(vp, wzv, E[o]);
             }
         }
         // evidence of (target, training galaxy t) over this z-chunk

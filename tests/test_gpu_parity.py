@@ -183,10 +183,7 @@ def test_kernel_grids_match_reference(sdss):
 # ------------------------------------------------------------------------------------------------
 def _check_fused(res, ref, K, atol_scale=1e-290):
     pdf_ref = ref["pdf"]
-    scale = pdf_ref.max(axis=1, keepdims=True)
-    np.testing.assert_allclose(res["pdf"], pdf_ref, rtol=RTOL, atol=0,
-                               err_msg="pdf") if atol_scale == 0 else \
-        assert_close(res["pdf"], pdf_ref, scale * atol_scale)
+    assert_close(res["pdf"], pdf_ref, pdf_ref.max(axis=1, keepdims=True) * atol_scale)
     if ref.get("evid") is not None and res.get("evid") is not None:
         assert_close(res["evid"], ref["evid"], ref["evid"].max(axis=1, keepdims=True) * atol_scale)
     if K:
@@ -350,10 +347,15 @@ def test_fused_full_size_properties():
     b = apply.apply_fused(grid, prior, zgrid, apply.Targets.full(fl, fv), ell_var=0.25, K=50,
                           nsplit=4)
     np.testing.assert_allclose(a["pdf"], b["pdf"], rtol=1e-11, atol=1e-290)
-    np.testing.assert_array_equal(a["top_idx"], b["top_idx"])
+    # evidences next to the underflow boundary may flush to zero along one path and not the
+    # other (then they tie at 0): compare the ranking where the evidence is representable
+    solid = a["top_ev"] > 1e-250 * a["top_ev"][:, :1]
+    assert solid.sum() > nO
+    np.testing.assert_array_equal(a["top_idx"][solid], b["top_idx"][solid])
+    np.testing.assert_allclose(a["top_ev"][solid], b["top_ev"][solid], rtol=1e-11)
     perm = rng.permutation(nO)
     c = apply.apply_fused(grid, prior, zgrid, apply.Targets.full(fl[perm], fv[perm]),
-                          ell_var=0.25, K=50)
+                          ell_var=0.25, K=50, nsplit=1)      # same split as `a`: bit-exact
     np.testing.assert_array_equal(c["pdf"], a["pdf"][perm])
     np.testing.assert_array_equal(c["top_idx"], a["top_idx"][perm])
     np.testing.assert_array_equal(a["pdf"][0], a["pdf"][1])
