@@ -53,6 +53,7 @@ _SIGS = {
     "dl_timing_enable": [c_i],
     "dl_timing_collect": [c_p, c_p],
     "dl_fp64_peak": [c_i, c_p],
+    "dl_selftest_math_dev": [c_ll, c_p, c_p, c_p],
 }
 _RESTYPES = {"dl_fused_padded_nz": c_ll, "dl_launch_count": c_ll, "dl_fused_workspace_bytes": c_ll,
              "dl_last_error": ctypes.c_char_p}

@@ -38,7 +38,8 @@ def build(force=False, verbose=False):
     procs = []
     for s in srcs:
         o = s[:-3] + ".o"
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+        cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("DL_NVCC_DEFS", "").split() + \
+            (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                                             text=True)))
         objs.append(o)

@@ -38,36 +38,33 @@ void dl_timing_mark(cudaStream_t stream, int which);  // 0 = before, 1 = after t
 namespace dl {
 
 // ------------------------------------------------------------------ FP64 fast-path arithmetic
-// MUFU.RCP64H seed (~20 bits) + two Newton steps on the FP64 pipe.  Valid for normal, positive
-// finite inputs (variances, sums of squares); no special-case branches.  ~1 ulp.
+// MUFU.RCP64H seed + ONE third-order step x1 = x0 (1 + e + e^2), e = 1 - d x0: 3 dependent FP64
+// ops.  The relative error is e^3; with the seed's measured |e| <= 2^-19.9 (tests/test_gpu_parity.py::
+// test_fast_math_accuracy) that is < 2^-59, i.e. limited by the final rounding.  Valid for
+// normal, positive finite inputs (variances, sums of squares); no special-case branches.
 __device__ __forceinline__ double rcp_fast(double d) {
     double x;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
-    double e = fma(-d, x, 1.0);
-    x = fma(x, e, x);
-    e = fma(-d, x, 1.0);
-    x = fma(x, e, x);
-    return x;
+    const double e = fma(-d, x, 1.0);
+    const double t = fma(e, e, e);
+    return fma(x, t, x);
 }
 
-// MUFU.RSQ64H seed + two coupled Newton steps.  Same validity domain as rcp_fast.
+// MUFU.RSQ64H seed + one third-order step y1 = y0 (1 + h/2 + 3 h^2 / 8), h = 1 - d y0^2
+// (5 dependent FP64 ops, error ~ h^3 / 3).  Same validity domain as rcp_fast.
 __device__ __forceinline__ double rsqrt_fast(double d) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
-    double g = d * y;           // ~sqrt(d)
-    double h = 0.5 * y;         // ~1/(2 sqrt(d))
-    double r = fma(-g, h, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    r = fma(-g, h, 0.5);
-    h = fma(h, r, h);
-    return h + h;
+    const double t = d * y;
+    const double h = fma(-t, y, 1.0);
+    const double q = fma(h, 0.375, 0.5);
+    return fma(y, h * q, y);
 }
 
 // exp(x) for x <= 0 (-inf / x < -708 -> 0: results that would be denormal are flushed; NaN
 // propagates).  Range reduction x = n ln2 + r, |r| <= ln2/2, degree-11 Taylor polynomial
-// (truncation 6e-15 relative, far below the 1e-9 parity contract), scaling through the
-// exponent field.
+// (truncation 6e-15 relative, far below the 1e-9 parity contract) evaluated as even + r * odd
+// parts in r^2 (two independent Horner chains of depth 5), scaling through the exponent field.
 __device__ __forceinline__ double exp_nonpos(double x) {
     const double L2E = 1.4426950408889634074;
     const double LN2_HI = 6.93147180369123816490e-01;
@@ -78,18 +75,20 @@ __device__ __forceinline__ double exp_nonpos(double x) {
     double fn = t - SHIFT;
     double r = fma(-fn, LN2_HI, x);
     r = fma(-fn, LN2_LO, r);
-    double p = 2.50521083854417187751e-08;             // 1/11!
-    p = fma(p, r, 2.75573192239858906526e-07);         // 1/10!
-    p = fma(p, r, 2.75573192239858906526e-06);         // 1/9!
-    p = fma(p, r, 2.48015873015873015873e-05);         // 1/8!
-    p = fma(p, r, 1.98412698412698412698e-04);         // 1/7!
-    p = fma(p, r, 1.38888888888888888889e-03);         // 1/6!
-    p = fma(p, r, 8.33333333333333333333e-03);         // 1/5!
-    p = fma(p, r, 4.16666666666666666667e-02);         // 1/4!
-    p = fma(p, r, 1.66666666666666666667e-01);         // 1/3!
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
+    const double r2 = r * r;
+    double pe = 2.75573192239858906526e-07;            // 1/10!
+    double po = 2.50521083854417187751e-08;            // 1/11!
+    pe = fma(pe, r2, 2.48015873015873015873e-05);      // 1/8!
+    po = fma(po, r2, 2.75573192239858906526e-06);      // 1/9!
+    pe = fma(pe, r2, 1.38888888888888888889e-03);      // 1/6!
+    po = fma(po, r2, 1.98412698412698412698e-04);      // 1/7!
+    pe = fma(pe, r2, 4.16666666666666666667e-02);      // 1/4!
+    po = fma(po, r2, 8.33333333333333333333e-03);      // 1/5!
+    pe = fma(pe, r2, 0.5);
+    po = fma(po, r2, 1.66666666666666666667e-01);      // 1/3!
+    pe = fma(pe, r2, 1.0);
+    po = fma(po, r2, 1.0);
+    const double p = fma(po, r, pe);
     // scale by 2^n through the exponent bits; results below 2^-1021 flush to zero
     int hi = __double2hiint(p) + (n << 20);
     double res = __hiloint2double(hi, __double2loint(p));

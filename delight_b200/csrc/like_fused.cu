@@ -32,16 +32,37 @@
 
 namespace dl {
 
-constexpr int FW = 8;             // compute warps per CTA
-constexpr int FTO = 4;            // targets per compute warp
+#ifndef DL_FW
+#define DL_FW 8
+#endif
+#ifndef DL_FTO
+#define DL_FTO 4
+#endif
+#ifndef DL_ZJ
+#define DL_ZJ 2
+#endif
+#ifndef DL_STAGES
+#define DL_STAGES 4
+#endif
+#ifndef DL_MINB
+#define DL_MINB 2
+#endif
+#ifndef DL_PRODUCER
+#define DL_PRODUCER 0
+#endif
+constexpr int FW = DL_FW;         // compute warps per CTA
+constexpr int FTO = DL_FTO;       // targets per compute warp
 constexpr int FZT = 4;            // redshifts per lane
+constexpr int ZJ = DL_ZJ;         // redshifts a lane processes jointly (independent chains)
 constexpr int FZC = 32 * FZT;     // redshifts per CTA chunk
-constexpr int FSTAGES = 4;        // TMA ring depth
+constexpr int FSTAGES = DL_STAGES;  // TMA ring depth
+constexpr int FPREF = FSTAGES - 2;  // prefetch distance in steps
 constexpr int FTPC = FW * FTO;    // targets per CTA
 constexpr int FTHREADS = FW * 32;
 constexpr int MAXNF = 8;
 
-__host__ __device__ constexpr int tc_stride(int nf) { return (5 * nf + 6 + 1) & ~1; }
+// per-target constants: [f][2] = (a', w') | [f][4] = (var', obs, obs^2, 0) | hc ic pOT pTT pOO c
+__host__ __device__ constexpr int tc_stride(int nf) { return 6 * nf + 6; }
 
 struct FusedParams {
     const double* grid;    // [nT][2*nB][nzp]  rows 0..nB-1 mean, nB..2nB-1 variance
@@ -58,17 +79,19 @@ struct FusedParams {
 };
 
 template <int NF, bool ZDEP>
-__global__ void __launch_bounds__(FTHREADS, 2) fused_like_kernel(const FusedParams p) {
+__global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const FusedParams p) {
     constexpr int ROWS = 2 * NF + 1;
     constexpr int TCS = tc_stride(NF);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stage = reinterpret_cast<double*>(smem_raw);        // [FSTAGES][ROWS][FZC]
     double* pdf_sm = stage + FSTAGES * ROWS * FZC;              // [FTPC][FZC]
     double* tc_sm = pdf_sm + FTPC * FZC;                        // [FTPC][TCS]
-    double* wz_sm = tc_sm + FTPC * TCS;                         // [FZC]
+    double* rv_sm = tc_sm + FTPC * TCS;                         // [FTPC][2]  (R, V) per target
+    double* wz_sm = rv_sm + FTPC * 2;                           // [FZC]
     double* zd_sm = wz_sm + FZC;                                // [4][FZC] (ZDEP only)
     uint64_t* full = reinterpret_cast<uint64_t*>(zd_sm + (ZDEP ? 4 * FZC : 0));
     uint64_t* empty = full + FSTAGES;
+    int* next_issue = reinterpret_cast<int*>(empty + FSTAGES);
 
     const int chunk = blockIdx.x % p.nchunk;
     const int otile = blockIdx.x / p.nchunk;
@@ -92,6 +115,7 @@ __global__ void __launch_bounds__(FTHREADS, 2) fused_like_kernel(const FusedPara
         tc_sm[i] = p.tconst[(size_t)o * TCS + (i % TCS)];
     }
     for (int i = threadIdx.x; i < FTPC * FZC; i += FTHREADS) pdf_sm[i] = 0.0;
+    for (int i = threadIdx.x; i < FTPC; i += FTHREADS) { rv_sm[2 * i] = -1e300; rv_sm[2 * i + 1] = 0.0; }
     for (int i = threadIdx.x; i < FZC; i += FTHREADS) {
         wz_sm[i] = p.wz[z0 + i];
         if (ZDEP) {
@@ -102,9 +126,9 @@ __global__ void __launch_bounds__(FTHREADS, 2) fused_like_kernel(const FusedPara
     __syncthreads();
 
     // ---------------------------------------------------------------------- TMA producer
-    // Lane 0 of warp 0 doubles as the producer: before computing step `it` it refills the stage
-    // that every warp released two steps ago (prefetch distance FSTAGES-2 steps, so it does not
-    // wait on warps that are still inside the previous step).
+    // No dedicated producer warp: whichever warp reaches step `it` first claims (smem CAS) the
+    // refill of step it + FPREF and its lane 0 issues the copies, so the fastest warp drives the
+    // ring and nobody waits on a lagging producer.
     const int nsteps = t_end - t_begin;
     auto issue_stage = [&](int step) {
         const int s = step % FSTAGES;
@@ -125,156 +149,185 @@ __global__ void __launch_bounds__(FTHREADS, 2) fused_like_kernel(const FusedPara
                      FZC * sizeof(double), &full[s]);
     };
     if (threadIdx.x == 0) {
-        for (int step = 0; step < FSTAGES - 2 && step < nsteps; ++step) issue_stage(step);
+        int step = 0;
+        for (; step < FPREF && step < nsteps; ++step) issue_stage(step);
+        *next_issue = step;
     }
+    __syncthreads();
 
-    // ---------------------------------------------------------------------- compute warps
-    double R[FTO], V[FTO], E[FTO];
+    // ---------------------------------------------------------------------- compute
+    // Each lane works on PAIRS of redshifts (z, z+32) of the chunk for one target at a time:
+    // the target's constants are fetched once (broadcast LDS.128) for two cells and every
+    // statement below carries two independent dependency chains for the FP64 pipe.
+    double E[FTO];
 #pragma unroll
-    for (int o = 0; o < FTO; ++o) { R[o] = -1e300; V[o] = 0.0; E[o] = 0.0; }
+    for (int o = 0; o < FTO; ++o) E[o] = 0.0;
     const double* tcw = tc_sm + warp * FTO * TCS;
     double* pdfw = pdf_sm + warp * FTO * FZC;
+    double* rvw = rv_sm + warp * FTO * 2;
     const int og0 = otile * FTPC + warp * FTO;
 
     int it = 0;
     for (int t = t_begin; t < t_end; ++t, ++it) {
         const int s = it % FSTAGES;
         const uint32_t ph = (it / FSTAGES) & 1;
-        if (threadIdx.x == 0 && it + FSTAGES - 2 < nsteps) issue_stage(it + FSTAGES - 2);
+#if DL_PRODUCER == 1
+        if (lane == 0) {
+            const int want = it + FPREF;
+            if (want < nsteps && atomicCAS(next_issue, want, want + 1) == want) issue_stage(want);
+        }
+#else
+        if (threadIdx.x == 0 && it + FPREF < nsteps) issue_stage(it + FPREF);
+#endif
         __syncwarp();
         mbar_wait(&full[s], ph);
         const double* st = stage + s * ROWS * FZC;
 #pragma unroll 1
-        for (int zi = 0; zi < FZT; ++zi) {
-            const int zl = zi * 32 + lane;
-            double m[NF], cv[NF], m2[NF];
+        for (int grp = 0; grp < FZT / ZJ; ++grp) {
+            const int zl = grp * 32 * ZJ + lane;      // cells: zl + 32 c, c < ZJ
+            double m[ZJ][NF], cv[ZJ][NF];
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
-                m[f] = st[f * FZC + zl];
-                cv[f] = st[(NF + f) * FZC + zl];
-                m2[f] = m[f] * m[f];
+#pragma unroll
+                for (int c = 0; c < ZJ; ++c) {
+                    m[c][f] = st[f * FZC + zl + 32 * c];
+                    cv[c][f] = st[(NF + f) * FZC + zl + 32 * c];
+                }
             }
-            const double pr = st[2 * NF * FZC + zl];
-            const double wzv = wz_sm[zl];
-            // padded redshifts get x = -inf: they never move R or V and contribute exactly 0
-            const double xmask = ((z0 + zl) < p.nz) ? 0.0 : -INFINITY;
-            double zot = 0, ztt = 0, zoo = 0, zev = 1.0;
-            if (ZDEP) {
-                zot = zd_sm[zl]; ztt = zd_sm[FZC + zl]; zoo = zd_sm[2 * FZC + zl];
-                zev = zd_sm[3 * FZC + zl];
+            double pr[ZJ], wzv[ZJ], xmask[ZJ], zot[ZJ], ztt[ZJ], zoo[ZJ], zev[ZJ];
+#pragma unroll
+            for (int c = 0; c < ZJ; ++c) {
+                pr[c] = st[2 * NF * FZC + zl + 32 * c];
+                wzv[c] = wz_sm[zl + 32 * c];
+                // padded redshifts get x = -inf: they never move R or V and contribute exactly 0
+                xmask[c] = ((z0 + zl + 32 * c) < p.nz) ? 0.0 : -INFINITY;
+                zot[c] = ztt[c] = zoo[c] = 0.0; zev[c] = 1.0;
+                if (ZDEP) {
+                    zot[c] = zd_sm[zl + 32 * c]; ztt[c] = zd_sm[FZC + zl + 32 * c];
+                    zoo[c] = zd_sm[2 * FZC + zl + 32 * c]; zev[c] = zd_sm[3 * FZC + zl + 32 * c];
+                }
             }
-            // ---- phase A: branch-free; written as three sweeps over the warp's FTO targets so
-            //      that each sweep offers FTO (or FTO x NF) independent dependency chains to the
-            //      FP64 pipe (the kernel is latency-bound otherwise: 4 warps per scheduler).
-            double x[FTO], y[FTO], sarg[FTO];
-            double e2[FTO];
-            // A1 -- pass 0: observed variances only (utils_cy.pyx:101-113 with ellML = 0)
 #pragma unroll
             for (int o = 0; o < FTO; ++o) {
                 const double* tc = tcw + o * TCS;
-                double fot, ftt;
-                if (ZDEP) {
-                    const double c = tc[5 * NF + 5];
-                    fot = c * zot; ftt = c * ztt;
-                } else {
-                    fot = tc[5 * NF + 2]; ftt = tc[5 * NF + 3];
-                }
+                const double hc = tc[6 * NF + 0], ic = tc[6 * NF + 1];
+                double pOT[ZJ], pTT[ZJ], pOO[ZJ];
 #pragma unroll
-                for (int f = 0; f < NF; ++f) {
-                    fot = fma(m[f], tc[f], fot);
-                    ftt = fma(m2[f], tc[NF + f], ftt);
-                }
-                const double ell = fot * rcp_fast(ftt);
-                e2[o] = ell * (ell * tc[5 * NF + 1]);
-            }
-            // A2 -- pass 1: variance inflated by ell^2 * model variance (utils_cy.pyx:107-112)
-            double sot[FTO], stt[FTO], soo[FTO], P[FTO];
-#pragma unroll
-            for (int o = 0; o < FTO; ++o) {
-                const double* tc = tcw + o * TCS;
-                double fot, ftt, foo;
-                if (ZDEP) {
-                    const double c = tc[5 * NF + 5];
-                    fot = c * zot; ftt = c * ztt; foo = c * zoo;
-                } else {
-                    fot = tc[5 * NF + 2]; ftt = tc[5 * NF + 3]; foo = tc[5 * NF + 4];
-                }
-                double pp = zev;
-#pragma unroll
-                for (int f = 0; f < NF; ++f) {
-                    const double var = fma(e2[o], cv[f], tc[2 * NF + f]);
-                    const double r = rcp_fast(var);
-                    const double tm = m[f] * r;
-                    fot = fma(tm, tc[3 * NF + f], fot);
-                    ftt = fma(tm, m[f], ftt);
-                    foo = fma(tc[4 * NF + f], r, foo);
-                    pp *= var;
-                }
-                sot[o] = fot; stt[o] = ftt; soo[o] = foo; P[o] = pp;
-            }
-            // A3 -- chi2 and (det)^-1/2 (utils_cy.pyx:111-118)
-#pragma unroll
-            for (int o = 0; o < FTO; ++o) {
-                const double hc = tcw[o * TCS + 5 * NF + 0];
-                y[o] = rsqrt_fast(P[o] * stt[o]);
-                const double rF = (y[o] * y[o]) * P[o];      // 1 / FTT
-                const double chi2 = fma(-(sot[o] * rF), sot[o], soo[o]);
-                x[o] = fma(hc, chi2, xmask);                 // -chi2/2 in the target's units
-                sarg[o] = x[o] - R[o];
-            }
-            // ---- phase B: rare -- the warp met a better cell than a reference exponent
-            {
-                bool up = false;
-#pragma unroll
-                for (int o = 0; o < FTO; ++o) up |= __double2hiint(sarg[o]) > 0;
-                if (__any_sync(0xffffffffu, up)) {
-#pragma unroll
-                    for (int o = 0; o < FTO; ++o) {
-                        if (__any_sync(0xffffffffu, sarg[o] > 0.0)) {
-                            const double xm = warp_max(x[o]);
-                            const double fs = exp(R[o] - xm);
-                            R[o] = xm; V[o] *= fs; E[o] *= fs;
-#pragma unroll
-                            for (int zj = 0; zj < FZT; ++zj) pdfw[o * FZC + zj * 32 + lane] *= fs;
-                            sarg[o] = x[o] - xm;
-                        }
+                for (int c = 0; c < ZJ; ++c) {
+                    if (ZDEP) {
+                        const double cc = tc[6 * NF + 5];
+                        pOT[c] = cc * zot[c]; pTT[c] = cc * ztt[c]; pOO[c] = cc * zoo[c];
+                    } else {
+                        pOT[c] = tc[6 * NF + 2]; pTT[c] = tc[6 * NF + 3]; pOO[c] = tc[6 * NF + 4];
                     }
                 }
-            }
-            // ---- phase C: exp, FTO independent chains                 (:118,128 up to scale)
-            double v[FTO];
+                // pass 0: observed variances only (utils_cy.pyx:101-113 with ellML = 0)
+                double fot[ZJ], ftt[ZJ], foo[ZJ], P[ZJ], e2[ZJ];
 #pragma unroll
-            for (int o = 0; o < FTO; ++o) v[o] = exp_nonpos(sarg[o]) * y[o];
-            // ---- phase D: running max of the un-priored value (both operands are >= 0, so the
-            //      comparison is done on the bit patterns by the integer pipe)
-            {
+                for (int c = 0; c < ZJ; ++c) { fot[c] = pOT[c]; ftt[c] = pTT[c]; }
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    const double a = tc[2 * f], w = tc[2 * f + 1];
+#pragma unroll
+                    for (int c = 0; c < ZJ; ++c) {
+                        const double tw = m[c][f] * w;
+                        fot[c] = fma(m[c][f], a, fot[c]);
+                        ftt[c] = fma(tw, m[c][f], ftt[c]);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < ZJ; ++c) {
+                    const double ell = fot[c] * rcp_fast(ftt[c]);
+                    e2[c] = ell * (ell * ic);
+                    fot[c] = pOT[c]; ftt[c] = pTT[c]; foo[c] = pOO[c]; P[c] = zev[c];
+                }
+                // pass 1: variance inflated by ell^2 * model variance (utils_cy.pyx:107-112)
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    const double ov = tc[2 * NF + 4 * f], ob = tc[2 * NF + 4 * f + 1],
+                                 o2 = tc[2 * NF + 4 * f + 2];
+#pragma unroll
+                    for (int c = 0; c < ZJ; ++c) {
+                        const double var = fma(e2[c], cv[c][f], ov);
+                        const double r = rcp_fast(var);
+                        const double tm = m[c][f] * r;
+                        fot[c] = fma(tm, ob, fot[c]);
+                        ftt[c] = fma(tm, m[c][f], ftt[c]);
+                        foo[c] = fma(o2, r, foo[c]);
+                        P[c] *= var;
+                    }
+                }
+                // chi2 and (det)^-1/2 (utils_cy.pyx:111-118)
+                double x[ZJ], y[ZJ], sarg[ZJ];
+                const double R = rvw[2 * o];
+#pragma unroll
+                for (int c = 0; c < ZJ; ++c) {
+                    y[c] = rsqrt_fast(P[c] * ftt[c]);
+                    const double rF = (y[c] * y[c]) * P[c];      // 1 / FTT
+                    const double chi2 = fma(-(fot[c] * rF), fot[c], foo[c]);
+                    x[c] = fma(hc, chi2, xmask[c]);              // -chi2/2 in the target's units
+                    sarg[c] = x[c] - R;
+                }
                 bool up = false;
 #pragma unroll
-                for (int o = 0; o < FTO; ++o)
-                    up |= __double_as_longlong(v[o]) > __double_as_longlong(V[o]);
+                for (int c = 0; c < ZJ; ++c) up |= __double2hiint(sarg[c]) > 0;
                 if (__any_sync(0xffffffffu, up)) {
+                    // rare: the warp met a better cell than its reference exponent
+                    double xl = x[0];
 #pragma unroll
-                    for (int o = 0; o < FTO; ++o) V[o] = fmax(V[o], warp_max(v[o]));
+                    for (int c = 1; c < ZJ; ++c) xl = fmax(xl, x[c]);
+                    const double xm = warp_max(xl);
+                    if (xm > R) {
+                        const double fs = exp(R - xm);
+                        E[o] *= fs;
+#pragma unroll
+                        for (int zj = 0; zj < FZT; ++zj) pdfw[o * FZC + zj * 32 + lane] *= fs;
+                        __syncwarp();
+                        if (lane == 0) { rvw[2 * o] = xm; rvw[2 * o + 1] *= fs; }
+                        __syncwarp();
+#pragma unroll
+                        for (int c = 0; c < ZJ; ++c) sarg[c] = x[c] - xm;
+                    }
                 }
-            }
-            // ---- phase E: prior, PDF and evidence accumulation  (delight-apply.py:145-148)
+                double v[ZJ];
 #pragma unroll
-            for (int o = 0; o < FTO; ++o) {
-                const double vp = v[o] * pr;
-                pdfw[o * FZC + zl] += vp;
-                E[o] = fma(vp, wzv, E[o]);
+                for (int c = 0; c < ZJ; ++c) v[c] = exp_nonpos(sarg[c]) * y[c];   // :118,128
+                // running max of the un-priored value (operands >= 0: compare bit patterns on
+                // the integer pipe)
+                const double V = rvw[2 * o + 1];
+                up = false;
+#pragma unroll
+                for (int c = 0; c < ZJ; ++c)
+                    up |= __double_as_longlong(v[c]) > __double_as_longlong(V);
+                if (__any_sync(0xffffffffu, up)) {
+                    double vl = v[0];
+#pragma unroll
+                    for (int c = 1; c < ZJ; ++c) vl = fmax(vl, v[c]);
+                    const double vm = warp_max(vl);
+                    __syncwarp();
+                    if (lane == 0) rvw[2 * o + 1] = fmax(V, vm);
+                    __syncwarp();
+                }
+                // prior, PDF and evidence accumulation  (delight-apply.py:145-148)
+#pragma unroll
+                for (int c = 0; c < ZJ; ++c) {
+                    const double vp = v[c] * pr[c];
+                    pdfw[o * FZC + zl + 32 * c] += vp;
+                    E[o] = fma(vp, wzv[c], E[o]);
+                }
             }
         }
         // evidence of (target, training galaxy t) over this z-chunk
 #pragma unroll
         for (int o = 0; o < FTO; ++o) E[o] = warp_sum(E[o]);
         {
-            double ev = E[0], rr = R[0];
+            double ev = E[0];
 #pragma unroll
-            for (int o = 1; o < FTO; ++o) if (lane == o) { ev = E[o]; rr = R[o]; }
+            for (int o = 1; o < FTO; ++o) if (lane == o) ev = E[o];
             const int og = og0 + lane;
             if (lane < FTO && og < p.nO)
-                p.evid_part[((size_t)chunk * p.nO + og) * p.nT + t] = make_double2(ev, rr);
+                p.evid_part[((size_t)chunk * p.nO + og) * p.nT + t] =
+                    make_double2(ev, rvw[2 * lane]);
         }
 #pragma unroll
         for (int o = 0; o < FTO; ++o) E[o] = 0.0;
@@ -291,8 +344,8 @@ __global__ void __launch_bounds__(FTHREADS, 2) fused_like_kernel(const FusedPara
             for (int zj = 0; zj < FZT; ++zj) dst[zj * 32 + lane] = pdfw[o * FZC + zj * 32 + lane];
             if (lane == 0) {
                 const size_t k = ((size_t)split * p.nchunk + chunk) * p.nO + og;
-                p.Rw[k] = R[o];
-                p.Vw[k] = V[o];
+                p.Rw[k] = rvw[2 * o];
+                p.Vw[k] = rvw[2 * o + 1];
             }
         }
     }
@@ -301,7 +354,7 @@ __global__ void __launch_bounds__(FTHREADS, 2) fused_like_kernel(const FusedPara
 // ------------------------------------------------------------------------------------------
 // per-target constants (see header comment): scaled by c = 2^round(mean log2 var)
 // in:  obs/var [nO][NF] (already restricted to the group's NF bands), ell_hat/ell_var scalars
-// out: tconst [nO][tc_stride(NF)] = a'(NF) w'(NF) var'(NF) obs(NF) obs^2(NF) hc ic pOT pTT pOO c
+// out: tconst [nO][tc_stride(NF)], layout documented at tc_stride()
 __global__ void prep_targets_kernel(int nO, int NF, const double* __restrict__ obs,
                                     const double* __restrict__ var, double ell_hat,
                                     double ell_var, double* __restrict__ tconst) {
@@ -318,19 +371,19 @@ __global__ void prep_targets_kernel(int nO, int NF, const double* __restrict__ o
         const double ob = obs[(size_t)o * NF + f];
         const double vs = var[(size_t)o * NF + f] * ic;
         const double w = 1.0 / vs;
-        tc[f] = ob * w;
-        tc[NF + f] = w;
-        tc[2 * NF + f] = vs;
-        tc[3 * NF + f] = ob;
-        tc[4 * NF + f] = ob * ob;
+        tc[2 * f] = ob * w;
+        tc[2 * f + 1] = w;
+        tc[2 * NF + 4 * f] = vs;
+        tc[2 * NF + 4 * f + 1] = ob;
+        tc[2 * NF + 4 * f + 2] = ob * ob;
+        tc[2 * NF + 4 * f + 3] = 0.0;
     }
-    tc[5 * NF + 0] = -0.5 * ic;
-    tc[5 * NF + 1] = ic;
-    tc[5 * NF + 2] = c * (ell_hat / ell_var);
-    tc[5 * NF + 3] = c / ell_var;
-    tc[5 * NF + 4] = c * (ell_hat * ell_hat / ell_var);
-    tc[5 * NF + 5] = c;
-    if (TCS > 5 * NF + 6) tc[5 * NF + 6] = 0.0;
+    tc[6 * NF + 0] = -0.5 * ic;
+    tc[6 * NF + 1] = ic;
+    tc[6 * NF + 2] = c * (ell_hat / ell_var);
+    tc[6 * NF + 3] = c / ell_var;
+    tc[6 * NF + 4] = c * (ell_hat * ell_hat / ell_var);
+    tc[6 * NF + 5] = c;
 }
 
 // combine the per-warp (R, V) of each target: Rfin = max R, Vfin = max V * exp(R - Rfin)
@@ -664,8 +717,8 @@ template <int NF, bool ZDEP>
 static int launch_fused_t(const FusedParams& p, cudaStream_t stream) {
     constexpr int ROWS = 2 * NF + 1;
     constexpr int TCS = tc_stride(NF);
-    const size_t smem = sizeof(double) * (FSTAGES * ROWS * FZC + FTPC * FZC + FTPC * TCS + FZC +
-                                          (ZDEP ? 4 * FZC : 0)) + 2 * FSTAGES * sizeof(uint64_t);
+    const size_t smem = sizeof(double) * (FSTAGES * ROWS * FZC + FTPC * FZC + FTPC * TCS + FTPC * 2 + FZC +
+                                          (ZDEP ? 4 * FZC : 0)) + 2 * FSTAGES * sizeof(uint64_t) + 16;
     auto kern = fused_like_kernel<NF, ZDEP>;
     DL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));

@@ -161,6 +161,8 @@ long long dl_launch_count(void);                 /* kernels launched by this lib
 int dl_timing_enable(int on);                    /* CUDA-event timing of the fused kernel */
 int dl_timing_collect(double* total_ms, int* launches);
 int dl_fp64_peak(int reps, double* tflops);      /* measured FP64 FMA peak of the device */
+/* accuracy self-test of the kernel's fast reciprocal / rsqrt / exp: out [5][n] (device) */
+int dl_selftest_math_dev(long long n, const double* x, double* out, void* stream);
 
 #ifdef __cplusplus
 }

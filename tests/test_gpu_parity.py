@@ -178,6 +178,30 @@ def test_kernel_grids_match_reference(sdss):
     np.testing.assert_allclose(KLd.cpu().numpy(), g["KLd"], rtol=RTOL, atol=1e-300)
 
 
+def test_fast_math_accuracy():
+    """The fused kernel's branch-free reciprocal / rsqrt / exp helpers: measured error bounds
+    (these justify the single third-order Newton step after the MUFU seed)."""
+    import torch
+    from delight_b200 import _lib
+    rng = np.random.default_rng(0)
+    x = np.concatenate([10.0 ** rng.uniform(-280, 280, 200000), rng.uniform(1, 4, 200000),
+                        rng.uniform(0, 708, 200000)])
+    d = torch.from_numpy(x).cuda()
+    out = torch.empty((5, x.size), dtype=torch.float64, device="cuda")
+    _lib.check(_lib.lib().dl_selftest_math_dev(x.size, _lib.ptr(d), _lib.ptr(out),
+                                              _lib.stream_ptr()))
+    o = out.cpu().numpy()
+    seed_rcp = np.abs(o[3] * x - 1).max()
+    seed_rsq = np.abs(o[4] * o[4] * x - 1).max()
+    assert seed_rcp < 2.0 ** -19 and seed_rsq < 2.0 ** -18, (seed_rcp, seed_rsq)
+    assert np.abs(o[0] * x - 1).max() < 4e-16
+    assert np.abs(o[1] / (1 / np.sqrt(x)) - 1).max() < 6e-16
+    ex = np.exp(-x)
+    ok = x < 707.5
+    assert np.abs(o[2][ok] / ex[ok] - 1).max() < 5e-14
+    assert np.all(o[2][x > 708.5] == 0)
+
+
 # ------------------------------------------------------------------------------------------------
 # fused apply path
 # ------------------------------------------------------------------------------------------------
