@@ -155,6 +155,33 @@ int dl_metrics_dev(long long nO, long long nz, const double* pdf, long long ld_p
                    const double* zgrid, const double* ztrue, double* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Batched per-training-galaxy GP (device pointers).  Model = kernel grids from
+ * dl_kernel_grids_dev on zGP (redshiftGridGP) / fzGrid (= 1 + zGP), template flux tables
+ * tmpl [nt][nB][nz] on the fine grid zgrid [nz] (<sed>_fluxredshiftmod.txt, io.py:263-277),
+ * hyper-parameters V_C, V_L.  Rows are the reference's gpparams rows (delight-learn.py:46,85-90):
+ *   [B, z, ell, bands(B), betas(nt), L_tril(B(B+1)/2 row-major lower), D(B), 0-padding]
+ *
+ * dl_gp_fit_dev      replaces the loop body of scripts/delight-learn.py:61-90
+ *                    (scalefree_flux_likelihood utils.py:179-193 + PhotozGP.setData/getCore
+ *                    photoz_gp.py:186-234).  nbands [nT], bands/Y/Yvar [nT][nB] left-packed.
+ * dl_gp_predict_dev  replaces scripts/delight-apply.py:89-98 (PhotozGP.setCore +
+ *                    predictAndInterpolate, photoz_gp.py:236-347); writes the fused layout
+ *                    grid [nT][2 nB][nzp] and the training redshifts.
+ * ---------------------------------------------------------------------------------------- */
+int dl_gp_fit_dev(long long nT, long long nB, long long nt, long long nzg, long long nz,
+                  const double* KC_grid, const double* KL_grid, const double* zGP,
+                  const double* fzGrid, const double* tmpl, const double* zgrid, double V_C,
+                  double V_L, const long long* nbands, const long long* bands, const double* z,
+                  const double* Y, const double* Yvar, double* rows, long long numCol,
+                  void* stream);
+int dl_gp_predict_dev(long long nT, long long nB, long long nt, long long nzg, long long nz,
+                      const double* KC_grid, const double* KL_grid, const double* KC_diag,
+                      const double* KL_diag, const double* zGP, const double* fzGrid,
+                      const double* tmpl, const double* zgrid, double V_C, double V_L,
+                      const double* rows, long long numCol, double* grid, double* train_z,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Measurement hooks (used by bench.py; no effect on results)
  * ---------------------------------------------------------------------------------------- */
 long long dl_launch_count(void);                 /* kernels launched by this library so far */

@@ -386,3 +386,75 @@ def test_fused_full_size_properties():
     assert (a["top_idx"][np.arange(nO), 0] == src).mean() > 0.9
     assert np.all(np.diff(a["top_ev"], axis=1) <= 0)
     assert np.isfinite(a["pdf"]).all() and (a["pdf"] >= 0).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# batched GP: learn (fit) and apply front half (predict) vs the reference's own outputs
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def gp_sdss(sdss):
+    from delight_b200 import gp
+    g = sdss
+    return gp.PhotozGPBatched(g["tmpl"], g["zgrid"], g["amp"], g["mu"], g["sig"], g["lines_pos"],
+                              float(g["V_C"]), float(g["V_L"]), float(g["alpha_C"]),
+                              float(g["alpha_L"]), g["zgridGP"])
+
+
+def test_gp_fit_matches_reference_learn(sdss, gp_sdss):
+    """dl_gp_fit_dev vs the rows written by the reference's delight-learn (incl. galaxies with
+    dropped bands): best template and band list exact, ell / Cholesky factor / residuals 1e-9."""
+    from delight_b200 import gp
+    g = sdss
+    cat = gp.catalogue(g["tr_flux"], g["tr_var"], g["tr_bands"], g["tr_nb"], g["tr_z"])
+    rows = gp_sdss.fit(cat)
+    ref = g["gp_rows"]
+    assert rows.shape == ref.shape
+    nt = g["tmpl"].shape[0]
+    for i in range(ref.shape[0]):
+        B = int(ref[i, 0])
+        assert rows[i, 0] == B and rows[i, 1] == ref[i, 1]
+        np.testing.assert_array_equal(rows[i, 3:3 + B], ref[i, 3:3 + B])
+        np.testing.assert_array_equal(rows[i, 3 + B:3 + B + nt], ref[i, 3 + B:3 + B + nt])
+        np.testing.assert_allclose(rows[i, 2], ref[i, 2], rtol=RTOL)
+        core, want = rows[i, 3 + B + nt:], ref[i, 3 + B + nt:]
+        np.testing.assert_allclose(core, want, rtol=RTOL, atol=1e-12 * np.abs(want).max())
+
+
+def test_gp_predict_matches_reference_model_grid(sdss, gp_sdss):
+    """dl_gp_predict_dev (setCore + predictAndInterpolate) vs the reference's model_mean /
+    model_covar, through the fused layout."""
+    g = sdss
+    grid, train_z = gp_sdss.predict(g["gp_rows"])
+    nz, nT, nB = g["model_mean"].shape
+    G = grid.grid.cpu().numpy()
+    mean = G[:, :nB, :nz].transpose(2, 0, 1)
+    var = G[:, nB:, :nz].transpose(2, 0, 1)
+    np.testing.assert_allclose(mean, g["model_mean"], rtol=RTOL)
+    # the variance is a difference of nearly equal terms (kd - k^T A^-1 k): relative accuracy
+    # is limited by that cancellation in the reference too
+    scale = np.abs(g["model_covar"]).max(axis=0, keepdims=True)
+    assert np.all(np.abs(var - g["model_covar"]) <= 1e-7 * np.abs(g["model_covar"]) + 1e-11 * scale)
+    np.testing.assert_array_equal(train_z.cpu().numpy(), g["gp_rows"][:, 1])
+    assert np.all(G[:, :nB, nz:] == 0) and np.all(G[:, nB:, nz:] == 1)
+
+
+def test_full_pipeline_learn_predict_apply(sdss, gp_sdss):
+    """catalogue -> fit -> predict -> fused apply, entirely on the device, vs the reference's
+    end-to-end outputs (PDFs, evidences, top-K, metrics)."""
+    from delight_b200 import apply, gp
+    g = sdss
+    cat = gp.catalogue(g["tr_flux"], g["tr_var"], g["tr_bands"], g["tr_nb"], g["tr_z"])
+    rows = gp_sdss.fit(cat, out_device=True)
+    grid, train_z = gp_sdss.predict(rows)
+    prior = grid.gaussian_prior(g["zgrid"], train_z, float(g["zPriorSigma"]))
+    t = apply.Targets(g["ta_flux"], g["ta_var"], g["ta_bands"], g["ta_nb"], g["ta_z"])
+    K = g["top_idx"].shape[1]
+    res = apply.apply_fused(grid, prior, g["zgrid"], t, ell_hat=1.0,
+                            ell_var=float(g["ellPriorSigma"]) ** 2, K=K, want_evid=True,
+                            want_metrics=True)
+    # end to end the model variance's cancellation noise (1e-7 relative on tiny variances)
+    # propagates to the likelihood: tolerance 1e-6 here; each stage alone is held to 1e-9 above
+    np.testing.assert_allclose(res["pdf"], g["pdfs"], rtol=1e-6, atol=1e-290 * g["pdfs"].max())
+    np.testing.assert_array_equal(res["top_idx"], g["top_idx"])
+    np.testing.assert_array_equal(res["metrics"][:, 7].astype(int), g["pdfs"].argmax(axis=1))
+    np.testing.assert_allclose(res["metrics"][:, :7], g["metrics"][:, :7], rtol=1e-6)
