@@ -119,11 +119,29 @@ def reference_step(cy_like, model_mean, model_covar, prior, zgrid, cat, first, c
     return out
 
 
-def host_model_grid(nT, data, nB):
-    """Same stand-in model grid as the GPU arm, built on the host."""
+def set_omp_threads(n):
+    """Thread count of the OpenMP runtime the reference's Cython modules use (libgomp)."""
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(int(n))
+    except OSError:
+        pass
+
+
+def reference_model_grid(nT, data):
+    """Mock training catalogue -> the reference's own learn and predictAndInterpolate
+    (scripts/delight-learn.py:61-90, scripts/delight-apply.py:84-98) on the host."""
     from delight_b200 import workloads
-    mean, var, zt = workloads.standin_model_grid(nT, data, seed=1, nB=nB, device="cpu")
-    return mean.numpy(), var.numpy(), zt
+    from oracle import ref_pipeline
+    nB = data["tmpl"].shape[1]
+    cat = workloads.mock_catalogue(nT, data, seed=1, ell=1e6)
+    set_omp_threads(1)      # the GP object's tiny prange loops are 30x slower with many threads
+    gp, f_mod = ref_pipeline.make_gp(data, workloads.HYPER)
+    bands = np.tile(np.arange(nB), (nT, 1))
+    rows = ref_pipeline.learn(gp, f_mod, cat["z"], bands, np.full(nT, nB), cat["fluxes"],
+                              cat["fluxes_var"])
+    mm, mc, zt = ref_pipeline.model_grid(gp, rows, data["zgrid"], data["tmpl"].shape[0])
+    set_omp_threads(os.cpu_count() or 1)
+    return mm, mc, zt
 
 
 def run_reference(args):
@@ -142,7 +160,9 @@ def run_reference(args):
     else:
         cy_like, kind = orc.approx_flux_likelihood_cy, "port"
     nT = args.train
-    model_mean, model_covar, zt = host_model_grid(nT, data, nB)
+    t_setup = time.perf_counter()
+    model_mean, model_covar, zt = reference_model_grid(nT, data)
+    t_setup = time.perf_counter() - t_setup
     zgrid = data["zgrid"]
     prior = orc.z_prior(zgrid, zt, Z_PRIOR_SIGMA)
     per_step = args.ref_targets
@@ -161,7 +181,9 @@ def run_reference(args):
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(N_TARGETS, nT, nz, nB),
-                   "inputs": "larger than L2 (model grid 2 x %.0f MB)" % (model_mean.nbytes / 1e6)},
+                   "inputs": "larger than L2 (model grid 2 x %.0f MB)" % (model_mean.nbytes / 1e6),
+                   "model_grid": "reference learn + predictAndInterpolate on %d mock training "
+                                 "galaxies, %.0f s on the host (untimed setup)" % (nT, t_setup)},
         "cpu_baseline": {"value": value, "unit": "galaxies/s", "cores": cores, "kind": kind,
                          "sample": "%d targets/step against the full %d x %d x %d grid, loop "
                                    "body of delight-apply.py:114-162 incl. its per-target "
@@ -177,8 +199,9 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------------------------
-def cpu_baseline_sample(data, nT, nB, budget_s=20.0):
-    """Reference loop body timed on the host cores of this box on a bounded sample."""
+def cpu_baseline_sample(data, model_mean, model_covar, zt, budget_s=20.0):
+    """Reference loop body timed on the host cores of this box on a bounded sample, against the
+    same model grid the GPU arm uses (downloaded in the script's [nz, nT, nB] layout)."""
     from delight_b200 import workloads
     from oracle import ref, oracle as orc
     if ref.available():
@@ -187,10 +210,11 @@ def cpu_baseline_sample(data, nT, nB, budget_s=20.0):
         kind = "reference"
     else:
         cy_like, kind = orc.approx_flux_likelihood_cy, "port"
-    model_mean, model_covar, zt = host_model_grid(nT, data, nB)
     zgrid = data["zgrid"]
+    nz, nT, nB = model_mean.shape
     prior = orc.z_prior(zgrid, zt, Z_PRIOR_SIGMA)
     cat = workloads.mock_catalogue(64, data, seed=2)
+    set_omp_threads(os.cpu_count() or 1)
     reference_step(cy_like, model_mean, model_covar, prior, zgrid, cat, 0, 1)     # warm
     n, t0 = 0, time.perf_counter()
     while n < 64 and (time.perf_counter() - t0 < budget_s or n < 3):
@@ -200,7 +224,7 @@ def cpu_baseline_sample(data, nT, nB, budget_s=20.0):
     return {"value": n / dt, "unit": "galaxies/s", "cores": os.cpu_count() or 1, "kind": kind,
             "sample": "%d targets against the full %d x %d x %d grid (loop body of "
                       "delight-apply.py:114-162 incl. its per-target fancy-index grid copies), "
-                      "%.1f s" % (n, zgrid.size, nT, nB, dt)}
+                      "%.1f s" % (n, nz, nT, nB, dt)}
 
 
 def run_b200(args):
@@ -220,10 +244,28 @@ def run_b200(args):
     zgrid = data["zgrid"]
     nz, nB = zgrid.size, data["tmpl"].shape[1]
     nT, nO = args.train, args.targets
-    mean, var, zt = workloads.standin_model_grid(nT, data, seed=1)           # replicated
-    grid = apply.ModelGrid.from_legacy(mean, var)
-    del mean, var
-    prior = grid.gaussian_prior(zgrid, zt, Z_PRIOR_SIGMA)
+    H = workloads.HYPER
+    # model grid, replicated on every GPU: mock training catalogue -> batched GP fit (learn)
+    # -> batched GP predict, all on the device
+    from delight_b200 import gp as gpmod
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev[0].record()
+    gpm = gpmod.PhotozGPBatched(data["tmpl"], zgrid, data["amp"], data["mu"], data["sig"],
+                                H["lines_pos"], H["V_C"], H["V_L"], H["alpha_C"], H["alpha_L"],
+                                data["zgridGP"])
+    ev[1].record()
+    tr = workloads.mock_catalogue(nT, data, seed=1, ell=1e6)
+    tcat = gpmod.catalogue(tr["fluxes"], tr["fluxes_var"], np.tile(np.arange(nB), (nT, 1)),
+                           np.full(nT, nB), tr["z"])
+    rows = gpm.fit(tcat, out_device=True)
+    ev[2].record()
+    grid, train_z = gpm.predict(rows)
+    ev[3].record()
+    torch.cuda.synchronize()
+    setup_ms = {"kernel_grids_ms": ev[0].elapsed_time(ev[1]),
+                "learn_ms_incl_h2d": ev[1].elapsed_time(ev[2]),
+                "predict_ms": ev[2].elapsed_time(ev[3])}
+    prior = grid.gaussian_prior(zgrid, train_z, Z_PRIOR_SIGMA)
     cat = workloads.mock_catalogue(nO, data, seed=100 + rank)                # this rank's shard
     targets = apply.Targets.full(cat["fluxes"], cat["fluxes_var"], cat["z"])
     ws = apply.FusedWorkspace()
@@ -325,7 +367,11 @@ def run_b200(args):
         }
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_baseline_sample(data, nT, nB)
+            G = grid.grid[:, :, :nz].cpu().numpy()                 # [nT, 2nB, nz]
+            mm = np.ascontiguousarray(G[:, :nB, :].transpose(2, 0, 1))
+            mc = np.ascontiguousarray(G[:, nB:, :].transpose(2, 0, 1))
+            del G
+            cpu = cpu_baseline_sample(data, mm, mc, train_z.cpu().numpy())
         line = {
             "metric": "galaxy-PDFs/sec", "value": value, "unit": "galaxies/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
@@ -333,8 +379,11 @@ def run_b200(args):
             "data": "synthetic",
             "config": {"workload": workload_name(nO, nT, nz, nB),
                        "targets_per_gpu": nO, "n_train": nT, "nz": nz, "bands": nB,
-                       "Ncompress": N_COMPRESS, "model_grid": "stand-in (template x smooth "
-                       "perturbation), replicated per GPU, %.2f GB" % (grid_bytes / 1e9),
+                       "Ncompress": N_COMPRESS,
+                       "model_grid": "device learn + predict of %d simulateWithSEDs-style mock "
+                                     "training galaxies, replicated per GPU, %.2f GB"
+                                     % (nT, grid_bytes / 1e9),
+                       "setup": setup_ms,
                        "l2": "inputs larger than L2 (model grid %.2f GB re-streamed per step)"
                              % (grid_bytes / 1e9),
                        "parallelism": "targets sharded by rank, no data-path collective"},

@@ -27,8 +27,16 @@ def interp_table(tmpl, zgrid, types, z):
     return tmpl[types, :, i] * (1 - w) + tmpl[types, :, i + 1] * w
 
 
-def mock_catalogue(n, data, seed, ell=1.0, noise=0.05, nB=None):
-    """simulateWithSEDs-style draw.  Returns dict(z, types, fluxes [n,nB], fluxes_var [n,nB])."""
+# hyper-parameters of tests/parametersTest.cfg:55-64 (the reference's shipped defaults)
+HYPER = dict(V_C=0.5, V_L=0.5, alpha_C=1e3, alpha_L=1e2, zPriorSigma=0.5, ellPriorSigma=0.5,
+             lines_pos=[6500.0, 5002.26, 3732.22], lines_width=[20.0, 20.0, 20.0],
+             extraFracFluxError=1e-5)
+
+
+def mock_catalogue(n, data, seed, ell=1.0, noise=0.05, nB=None, extra_frac=1e-5):
+    """simulateWithSEDs-style draw as the catalogue reader hands it on (io.py:349-351 adds
+    (extraFracFluxError * flux)^2 to every variance).
+    Returns dict(z, types, fluxes [n,nB], fluxes_var [n,nB])."""
     rng = np.random.default_rng(seed)
     zgrid, tmpl = data["zgrid"], data["tmpl"]
     nB = nB or tmpl.shape[1]
@@ -36,8 +44,8 @@ def mock_catalogue(n, data, seed, ell=1.0, noise=0.05, nB=None):
     types = rng.integers(0, tmpl.shape[0], n)
     true = ell * interp_table(tmpl[:, :nB], zgrid, types, z)
     sig = true * noise
-    return dict(z=z, types=types, fluxes=true + sig * rng.standard_normal(true.shape),
-                fluxes_var=sig ** 2)
+    fluxes = true + sig * rng.standard_normal(true.shape)
+    return dict(z=z, types=types, fluxes=fluxes, fluxes_var=sig ** 2 + (extra_frac * fluxes) ** 2)
 
 
 def standin_model_grid(nT, data, seed, nB=None, device="cuda"):

@@ -12,6 +12,9 @@ reference's Python layers need on this image and returns the impo
   * coloredlogs -> stub
 """
 import importlib
+import importlib.abc
+import importlib.machinery
+import importlib.util
 import os
 import sys
 import types
@@ -84,6 +87,32 @@ def available():
                                     for f in os.listdir(d))
 
 
+class _RefFinder(importlib.abc.MetaPathFinder):
+    """Imports `delight` / `delight.<mod>` from oracle/_ref/delight: compiled extension modules
+    (.so) and sourceless byte-code stored as <mod>.bc."""
+
+    def find_spec(self, fullname, path=None, target=None):
+        pkg_dir = os.path.join(REF_DIR, "delight")
+        if fullname == "delight":
+            init = os.path.join(pkg_dir, "__init__.bc")
+            loader = importlib.machinery.SourcelessFileLoader(fullname, init)
+            return importlib.util.spec_from_file_location(
+                fullname, init, loader=loader, submodule_search_locations=[pkg_dir])
+        if not fullname.startswith("delight.") or fullname.count(".") != 1:
+            return None
+        name = fullname.split(".")[1]
+        for f in os.listdir(pkg_dir):
+            if f.startswith(name + ".") and f.endswith(".so"):
+                fp = os.path.join(pkg_dir, f)
+                loader = importlib.machinery.ExtensionFileLoader(fullname, fp)
+                return importlib.util.spec_from_file_location(fullname, fp, loader=loader)
+        bc = os.path.join(pkg_dir, name + ".bc")
+        if os.path.exists(bc):
+            loader = importlib.machinery.SourcelessFileLoader(fullname, bc)
+            return importlib.util.spec_from_file_location(fullname, bc, loader=loader)
+        return None
+
+
 def load():
     """Import and return the reference `delight` package from oracle/_ref."""
     if not available():
@@ -92,8 +121,8 @@ def load():
     mod = sys.modules.get("delight")
     if mod is not None and not getattr(mod, "__file__", "").startswith(REF_DIR):
         raise ImportError("a different `delight` is already imported: %r" % (mod,))
-    if REF_DIR not in sys.path:
-        sys.path.insert(0, REF_DIR)
+    if not any(isinstance(f, _RefFinder) for f in sys.meta_path):
+        sys.meta_path.insert(0, _RefFinder())
     delight = importlib.import_module("delight")
     for sub in ("utils_cy", "photoz_kernels_cy", "utils", "io", "photoz_kernels", "photoz_gp"):
         importlib.import_module("delight." + sub)
@@ -101,5 +130,5 @@ def load():
 
 
 def script_path(name):
-    """Path of a byte-compiled reference script (run with `python <path> params.cfg`)."""
-    return os.path.join(REF_DIR, "scripts", name + ".pyc")
+    """Path of a byte-compiled reference script (run with runpy.run_path)."""
+    return os.path.join(REF_DIR, "scripts", name + ".bc")
