@@ -92,15 +92,17 @@ confidenceLevels: 0.1 0.50 0.68 0.95
 
 def make_workdir(wd, bands=SDSS, train_bands=None, refband=None, reference="/root/reference",
                  numObjects=100, noiseLevel=0.05, zmin=0.01, zmax=1.511, dz=0.002, nzGP=150,
-                 Ncompress=50, zPriorSigma=0.5, ellPriorSigma=0.5, numCoefs=7):
-    """Copy the needed data files to `wd` and write params.cfg; returns the cfg path."""
+                 Ncompress=50, zPriorSigma=0.5, ellPriorSigma=0.5, numCoefs=7, copy_data=True):
+    """Copy the needed data files to `wd` (copy_data=False: the caller provides the
+    pre-processed coefficient / flux-redshift files itself) and write params.cfg; returns the
+    cfg path."""
     os.makedirs(wd, exist_ok=True)
     os.makedirs(os.path.join(wd, "FILTERS"), exist_ok=True)
     os.makedirs(os.path.join(wd, "CWW_SEDs"), exist_ok=True)
-    for b in bands:
+    for b in bands if copy_data else []:
         shutil.copy(os.path.join(reference, "data", "FILTERS", b + ".res"),
                     os.path.join(wd, "FILTERS"))
-    for s in CWW:
+    for s in CWW if copy_data else []:
         shutil.copy(os.path.join(reference, "data", "CWW_SEDs", s + ".dat"),
                     os.path.join(wd, "CWW_SEDs"))
     train_bands = list(train_bands or bands)
@@ -122,10 +124,22 @@ def make_workdir(wd, bands=SDSS, train_bands=None, refband=None, reference="/roo
     return cfg
 
 
+def write_preprocessed(wd, bands, amp, mu, sig, tmpl, seds=CWW):
+    """Write <band>_gaussian_coefficients.txt and <sed>_fluxredshiftmod.txt (the outputs of
+    processFilters.py:57-62 / processSEDs.py:51) from arrays, e.g. from a golden fixture."""
+    import numpy as np
+    for ib, b in enumerate(bands):
+        np.savetxt(os.path.join(wd, "FILTERS", b + "_gaussian_coefficients.txt"),
+                   np.stack([amp[ib], mu[ib], sig[ib]], axis=1), header=b)
+    for it, s in enumerate(seds):
+        np.savetxt(os.path.join(wd, "CWW_SEDs", s + "_fluxredshiftmod.txt"), tmpl[it].T)
+
+
 _RUNNER = r"""
 import sys, warnings
 warnings.filterwarnings('ignore')
 sys.path.insert(0, {repo!r})
+{pre}
 from oracle import ref
 ref.load()
 import numpy as np
@@ -136,12 +150,16 @@ runpy.run_path({script!r}, run_name='__main__')
 """
 
 
-def run_script(name, cfg, seed=0, omp_threads=None, quiet=True):
-    """Run one byte-compiled reference script on `cfg` with the global NumPy RNG seeded."""
+def run_script(name, cfg, seed=0, omp_threads=None, quiet=True, dropin=False):
+    """Run one byte-compiled reference script on `cfg` with the global NumPy RNG seeded.
+    dropin=True first aliases delight_b200's CUDA operator modules as delight.utils_cy /
+    delight.photoz_kernels_cy (the script itself and the reference's Python layers are
+    unchanged)."""
     env = dict(os.environ)
     if omp_threads:
         env["OMP_NUM_THREADS"] = str(omp_threads)
-    code = _RUNNER.format(repo=REPO, seed=seed, script=ref.script_path(name), cfg=cfg)
+    pre = "import delight_b200.install; delight_b200.install.install()" if dropin else ""
+    code = _RUNNER.format(repo=REPO, seed=seed, script=ref.script_path(name), cfg=cfg, pre=pre)
     out = subprocess.run([sys.executable, "-c", code], env=env, cwd=os.path.dirname(cfg),
                          stdout=subprocess.PIPE if quiet else None,
                          stderr=subprocess.STDOUT if quiet else None, text=True)

@@ -289,6 +289,10 @@ def gen_sdss_pipeline(wd):
         n_read += 1
     for a in (pdfs, evid, top_idx, top_ev, metrics, ta_bands, ta_nb, ta_flux, ta_var, ta_z):
         a.resize((n_read,) + a.shape[1:], refcheck=False)
+    out.update(train_cat=tr, target_cat=ta,
+               train_bandOrder=np.array(" ".join(params["training_bandOrder"])),
+               target_bandOrder=np.array(" ".join(params["target_bandOrder"])),
+               Ncompress=K)
     out.update(prior=prior, pdfs=pdfs, evid=evid, top_idx=top_idx, top_ev=top_ev,
                metrics=metrics, ta_nb=ta_nb, ta_bands=ta_bands, ta_flux=ta_flux, ta_var=ta_var,
                ta_z=ta_z, like0=like0, confidenceLevels=np.array(params["confidenceLevels"]))

@@ -458,3 +458,40 @@ def test_full_pipeline_learn_predict_apply(sdss, gp_sdss):
     np.testing.assert_array_equal(res["top_idx"], g["top_idx"])
     np.testing.assert_array_equal(res["metrics"][:, 7].astype(int), g["pdfs"].argmax(axis=1))
     np.testing.assert_allclose(res["metrics"][:, :7], g["metrics"][:, :7], rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------
+# the drop-in property: the reference's own scripts, unchanged, on the CUDA operators
+# ------------------------------------------------------------------------------------------------
+def test_reference_scripts_run_unchanged_on_cuda_operators(sdss, tmp_path):
+    """delight-learn and delight-apply (byte-compiled, unmodified, with the reference's own io /
+    photoz_gp / photoz_kernels layers) run with delight_b200's modules registered as
+    delight.utils_cy / delight.photoz_kernels_cy and reproduce the reference's files."""
+    from oracle import pipeline, ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    g = sdss
+    wd = str(tmp_path)
+    K = int(g["Ncompress"])
+    cfg = pipeline.make_workdir(wd, bands=pipeline.SDSS,
+                                train_bands=["U_SDSS", "G_SDSS", "I_SDSS"], refband="I_SDSS",
+                                numObjects=24, dz=0.01, nzGP=40, Ncompress=K, copy_data=False)
+    pipeline.write_preprocessed(wd, pipeline.SDSS, g["amp"], g["mu"], g["sig"], g["tmpl"])
+    np.savetxt(wd + "/galaxies-fluxredshifts.txt", g["train_cat"])
+    np.savetxt(wd + "/galaxies-fluxredshifts2.txt", g["target_cat"])
+    out = pipeline.run_script("delight-learn", cfg, dropin=True)
+    assert "DELIGHT-LEARN" in out
+    rows = np.loadtxt(wd + "/galaxies-gpparams.txt")
+    np.testing.assert_allclose(rows, g["gp_rows"], rtol=1e-9, atol=1e-11 * np.abs(g["gp_rows"]).max())
+    out = pipeline.run_script("delight-apply", cfg, dropin=True)
+    assert "DELIGHT-APPLY" in out
+    pdfs = np.loadtxt(wd + "/redshiftpdfs.txt")                 # written with '%.2e'
+    np.testing.assert_allclose(pdfs, g["pdfs"], rtol=6e-3, atol=1e-300)
+    idx = np.loadtxt(wd + "/compressIndices.txt", dtype=np.int64)
+    ev = np.loadtxt(wd + "/compressLikes.txt")
+    np.testing.assert_allclose(ev, g["top_ev"], rtol=6e-3, atol=1e-300)
+    # the script sorts with NumPy's default (unstable) argsort: compare as sets per target
+    for o in range(idx.shape[0]):
+        assert set(idx[o]) == set(g["top_idx"][o])
+    met = np.loadtxt(wd + "/metrics.txt")
+    np.testing.assert_allclose(met, g["metrics"], rtol=6e-3, atol=1e-300)
