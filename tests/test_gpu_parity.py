@@ -495,3 +495,84 @@ def test_reference_scripts_run_unchanged_on_cuda_operators(sdss, tmp_path):
         assert set(idx[o]) == set(g["top_idx"][o])
     met = np.loadtxt(wd + "/metrics.txt")
     np.testing.assert_allclose(met, g["metrics"], rtol=6e-3, atol=1e-300)
+
+
+def test_gp_fit_g10_style_heterogeneous_bands(orc):
+    """Config-4 shape: 28 bands, every training galaxy keeps a random subset of 2..21 valid
+    bands (G10-style); device kernel grids + batched fit vs the NumPy/C oracle."""
+    from delight_b200 import gp
+    rng = np.random.default_rng(42)
+    nB, NC, nt, nzg, nz, nT = 28, 5, 4, 24, 120, 40
+    mu0 = np.linspace(3500, 22000, nB)
+    amp = rng.uniform(0.2, 1.0, (nB, NC))
+    mu = mu0[:, None] + np.linspace(-300, 300, NC)[None, :]
+    sig = rng.uniform(80, 200, (nB, NC))
+    lines = np.array([6500.0, 5002.26, 3732.22])
+    zgrid = np.linspace(0.01, 1.5, nz)
+    zgp = np.logspace(np.log10(0.01), np.log10(1.5 * 1.01), nzg)
+    tmpl = 1e-6 * rng.uniform(0.5, 2.0, (nt, nB, 1)) * (1 + 0.5 * np.sin(
+        zgrid[None, None, :] * rng.uniform(1, 5, (nt, nB, 1))))
+    V_C, V_L, aC, aL = 0.5, 0.5, 1e3, 1e2
+    gpm = gp.PhotozGPBatched(tmpl, zgrid, amp, mu, sig, lines, V_C, V_L, aC, aL, zgp)
+    grids = orc.kernel_grids(amp, mu, sig, lines, aC, aL, zgp)
+    np.testing.assert_allclose(gpm.KC.cpu().numpy(), grids["KC"], rtol=RTOL)
+    np.testing.assert_allclose(gpm.KL.cpu().numpy(), grids["KL"], rtol=RTOL, atol=1e-300)
+    z = rng.uniform(0.05, 1.45, nT)
+    types = rng.integers(0, nt, nT)
+    nb = rng.integers(2, 22, nT)
+    bands = np.zeros((nT, nB), dtype=np.int64)
+    fl = np.zeros((nT, nB))
+    fv = np.zeros((nT, nB))
+    for i in range(nT):
+        b = np.sort(rng.choice(nB, nb[i], replace=False))
+        bands[i, :nb[i]] = b
+        true = 1e6 * np.array([orc.interp_lin_extrap(zgrid, tmpl[types[i], bb], z[i])[0]
+                               for bb in b])
+        fv[i, :nb[i]] = (0.05 * true) ** 2
+        fl[i, :nb[i]] = true * (1 + 0.05 * rng.standard_normal(nb[i]))
+    rows = gpm.fit(gp.catalogue(fl, fv, bands, nb, z))
+    for i in range(nT):
+        B = int(nb[i])
+        ref = orc.gp_fit(grids, V_C, V_L, tmpl, zgrid, bands[i, :B], z[i], fl[i, :B], fv[i, :B])
+        assert rows[i, 0] == B
+        np.testing.assert_array_equal(rows[i, 3:3 + B], bands[i, :B])
+        assert int(np.argmax(rows[i, 3 + B:3 + B + nt])) == ref["bestType"]
+        np.testing.assert_allclose(rows[i, 2], ref["ell"], rtol=RTOL)
+        core = rows[i, 3 + B + nt:3 + B + nt + B * (B + 1) // 2 + B]
+        want = ref["core"][nt:]
+        np.testing.assert_allclose(core, want, rtol=1e-8, atol=1e-12 * np.abs(want).max())
+        assert np.all(rows[i, 3 + B + nt + B * (B + 1) // 2 + B:] == 0)
+
+
+def test_templatefit_config2_scale_properties():
+    """Config-2 shape (8 templates x 1500 z x 5 bands, many targets, explicit p(z,t) prior, no
+    model variance): tiled launches over a large target batch give the same rows as a small
+    batch, PDFs are finite and non-negative and the best-fit z of noiseless targets is mostly
+    the source redshift."""
+    from delight_b200 import apply, workloads
+    data = workloads.load_lsst()
+    zgrid, tmpl = data["zgrid"], data["tmpl"][:, :5]
+    nt, nB, nz = tmpl.shape
+    f_mod = np.ascontiguousarray(tmpl.transpose(2, 0, 1))                 # [nz, nt, nB]
+    b2 = data["p_z_t"] ** 2
+    p_z = data["p_t"][None, :] * zgrid[:, None] / b2[None, :] * np.exp(
+        -0.5 * zgrid[:, None] ** 2 / b2[None, :])
+    grid = apply.ModelGrid.from_legacy(f_mod, np.zeros_like(f_mod))
+    prior = grid.explicit_prior(p_z)
+    rng = np.random.default_rng(9)
+    nO = 20000
+    zi = rng.integers(50, nz - 50, nO)
+    ty = rng.integers(0, nt, nO)
+    fl = f_mod[zi, ty] * rng.uniform(0.5, 2.0, (nO, 1))
+    fv = (0.01 * fl) ** 2
+    ws = apply.FusedWorkspace(max_bytes=64 << 20)          # force several target tiles
+    res = apply.apply_fused(grid, prior, zgrid, apply.Targets.full(fl, fv), ell_hat=1.0,
+                            ell_var=1e24, K=0, want_metrics=True, workspace=ws)
+    assert res["fused_launches"] > 1
+    small = apply.apply_fused(grid, prior, zgrid, apply.Targets.full(fl[:64], fv[:64]),
+                              ell_hat=1.0, ell_var=1e24, K=0, nsplit=1)
+    np.testing.assert_allclose(res["pdf"][:64], small["pdf"], rtol=1e-11, atol=1e-290)
+    assert np.isfinite(res["pdf"]).all() and (res["pdf"] >= 0).all()
+    # noiseless targets: the posterior mode sits on the source redshift unless the p(z,t) prior
+    # or a template degeneracy moves it
+    assert (np.abs(res["metrics"][:, 7] - zi) <= 1).mean() > 0.5
