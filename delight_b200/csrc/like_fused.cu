@@ -50,6 +50,12 @@ namespace dl {
 #ifndef DL_PRODUCER
 #define DL_PRODUCER 0
 #endif
+#ifndef DL_ABL
+#define DL_ABL 0
+#endif
+#ifndef DL_PRODWARP
+#define DL_PRODWARP 0
+#endif
 constexpr int FW = DL_FW;         // compute warps per CTA
 constexpr int FTO = DL_FTO;       // targets per compute warp
 constexpr int FZT = 4;            // redshifts per lane
@@ -177,7 +183,7 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
             if (want < nsteps && atomicCAS(next_issue, want, want + 1) == want) issue_stage(want);
         }
 #else
-        if (threadIdx.x == 0 && it + FPREF < nsteps) issue_stage(it + FPREF);
+        if (threadIdx.x == DL_PRODWARP * 32 && it + FPREF < nsteps) issue_stage(it + FPREF);
 #endif
         __syncwarp();
         mbar_wait(&full[s], ph);
@@ -209,7 +215,14 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
             }
 #pragma unroll
             for (int o = 0; o < FTO; ++o) {
+#if DL_ABL & 1
+                double tcr[6 * NF + 6];          // ablation: constants without shared loads
+#pragma unroll
+                for (int q = 0; q < 6 * NF + 6; ++q) tcr[q] = 1.0 + 0.001 * (q + o);
+                const double* tc = tcr;
+#else
                 const double* tc = tcw + o * TCS;
+#endif
                 const double hc = tc[6 * NF + 0], ic = tc[6 * NF + 1];
                 double pOT[ZJ], pTT[ZJ], pOO[ZJ];
 #pragma unroll
@@ -271,7 +284,11 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
                 bool up = false;
 #pragma unroll
                 for (int c = 0; c < ZJ; ++c) up |= __double2hiint(sarg[c]) > 0;
+#if DL_ABL & 2
+                if (false) {
+#else
                 if (__any_sync(0xffffffffu, up)) {
+#endif
                     // rare: the warp met a better cell than its reference exponent
                     double xl = x[0];
 #pragma unroll
@@ -299,7 +316,11 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
 #pragma unroll
                 for (int c = 0; c < ZJ; ++c)
                     up |= __double_as_longlong(v[c]) > __double_as_longlong(V);
+#if DL_ABL & 2
+                if (false) {
+#else
                 if (__any_sync(0xffffffffu, up)) {
+#endif
                     double vl = v[0];
 #pragma unroll
                     for (int c = 1; c < ZJ; ++c) vl = fmax(vl, v[c]);
@@ -312,7 +333,9 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
 #pragma unroll
                 for (int c = 0; c < ZJ; ++c) {
                     const double vp = v[c] * pr[c];
+#if !(DL_ABL & 4)
                     pdfw[o * FZC + zl + 32 * c] += vp;
+#endif
                     E[o] = fma(vp, wzv[c], E[o]);
                 }
             }
