@@ -143,6 +143,8 @@ def _as_dev(a):
             raise ValueError("expected float64")
         return t.cuda().contiguous()
     a = np.ascontiguousarray(a, dtype=np.float64)
+    if not a.flags.writeable:
+        a = a.copy()
     return torch.from_numpy(a).cuda()
 
 
@@ -189,13 +191,16 @@ class FusedWorkspace:
 
 
 def apply_fused(grid, prior, zgrid, targets, ell_hat=1.0, ell_var=1.0, K=0, want_evid=False,
-                want_metrics=False, workspace=None, nsplit=None, out_device=False):
+                want_metrics=False, workspace=None, nsplit=None, out_device=False,
+                confidence_levels=None):
     """Likelihood + PDF + evidences + top-K for all `targets` against the whole model grid.
 
     ell_hat / ell_var: scalars (what delight-apply.py:119-144 passes: 1 and ellPriorSigma^2) or
     arrays [nz] (the general operator signature, utils_cy.pyx:92-93).
+    confidence_levels (with want_metrics): the cfg's confidenceLevels; the metrics then carry the
+    reference's 7 + nCL columns of computeMetrics (utils.py:213-227) followed by the argmax index.
     Returns dict(pdf [nO, nz], top_idx [nO, K] int64, top_ev [nO, K], evid [nO, nT] | None,
-    metrics [nO, 8] | None) as NumPy arrays (or CUDA tensors with out_device=True).
+    metrics [nO, 8 (+ nCL)] | None) as NumPy arrays (or CUDA tensors with out_device=True).
     """
     torch = _lib.require_cuda()
     L = _lib.lib()
@@ -280,6 +285,13 @@ def apply_fused(grid, prior, zgrid, targets, ell_hat=1.0, ell_var=1.0, K=0, want
         metrics = torch.empty((nO, 8), dtype=torch.float64, device="cuda")
         _lib.check(L.dl_metrics_dev(nO, nz, _lib.ptr(pdf), nz, _lib.ptr(zg), _lib.ptr(zt),
                                     _lib.ptr(metrics), _lib.stream_ptr()))
+        if confidence_levels is not None and len(confidence_levels):
+            # computeMetrics: CIlevel(grid, PDF, 1.0 - confI) per level  (utils.py:223-225)
+            fr = _as_dev(1.0 - np.asarray(confidence_levels, dtype=np.float64))
+            ci = torch.empty((nO, fr.numel()), dtype=torch.float64, device="cuda")
+            _lib.check(L.dl_ci_levels_dev(nO, nz, _lib.ptr(pdf), nz, _lib.ptr(zg), fr.numel(),
+                                          _lib.ptr(fr), 200, _lib.ptr(ci), _lib.stream_ptr()))
+            metrics = torch.cat([metrics[:, :7], ci, metrics[:, 7:]], dim=1)
     out = dict(pdf=pdf, top_idx=top_idx, top_ev=top_ev, evid=evid, metrics=metrics,
                fused_launches=launches)
     if not out_device:

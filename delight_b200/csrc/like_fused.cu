@@ -11,9 +11,9 @@
 //   CTA tile = one z-chunk of 128 redshifts  x  32 targets (4 per compute warp)
 //              x  a contiguous range of training galaxies (all of them unless nsplit > 1)
 //   lane     = 4 redshifts of the chunk (z = z0 + 32*j + lane) -> conflict-free smem rows
-//   producer = per training galaxy one pipeline stage: 2*NF+1 rows (NF band means, NF band
+//   staging  = per training galaxy one pipeline stage: 2*NF+1 rows (NF band means, NF band
 //              variances, the prior row) of 128 doubles each, fetched with 1-D TMA bulk copies
-//              (cp.async.bulk ... mbarrier::complete_tx) into a 4-deep full/empty mbarrier ring
+//              (cp.async.bulk ... mbarrier::complete_tx) into a full/empty mbarrier ring
 //   compute  = per (target, training galaxy, z) cell, all in FP64 on the vector pipe:
 //              pass 0 with the observed variances only (2 FMA / band, per-target constants
 //              broadcast from smem), one reciprocal for the luminosity scale, pass 1 with the
@@ -46,15 +46,6 @@ namespace dl {
 #endif
 #ifndef DL_MINB
 #define DL_MINB 2
-#endif
-#ifndef DL_PRODUCER
-#define DL_PRODUCER 0
-#endif
-#ifndef DL_ABL
-#define DL_ABL 0
-#endif
-#ifndef DL_PRODWARP
-#define DL_PRODWARP 0
 #endif
 constexpr int FW = DL_FW;         // compute warps per CTA
 constexpr int FTO = DL_FTO;       // targets per compute warp
@@ -97,7 +88,6 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
     double* zd_sm = wz_sm + FZC;                                // [4][FZC] (ZDEP only)
     uint64_t* full = reinterpret_cast<uint64_t*>(zd_sm + (ZDEP ? 4 * FZC : 0));
     uint64_t* empty = full + FSTAGES;
-    int* next_issue = reinterpret_cast<int*>(empty + FSTAGES);
 
     const int chunk = blockIdx.x % p.nchunk;
     const int otile = blockIdx.x / p.nchunk;
@@ -132,9 +122,10 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
     __syncthreads();
 
     // ---------------------------------------------------------------------- TMA producer
-    // No dedicated producer warp: whichever warp reaches step `it` first claims (smem CAS) the
-    // refill of step it + FPREF and its lane 0 issues the copies, so the fastest warp drives the
-    // ring and nobody waits on a lagging producer.
+    // No dedicated producer warp (it would cost 32 registers/thread of occupancy): lane 0 of
+    // warp 0 refills, before it computes step `it`, the stage every warp released FPREF steps
+    // ago.  (Measured alternatives: "first warp to arrive claims the refill" 2.8x slower -- the
+    // claimant sleeps in try_wait on the empty barrier; deeper rings 3-6 % slower.)
     const int nsteps = t_end - t_begin;
     auto issue_stage = [&](int step) {
         const int s = step % FSTAGES;
@@ -155,11 +146,8 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
                      FZC * sizeof(double), &full[s]);
     };
     if (threadIdx.x == 0) {
-        int step = 0;
-        for (; step < FPREF && step < nsteps; ++step) issue_stage(step);
-        *next_issue = step;
+        for (int step = 0; step < FPREF && step < nsteps; ++step) issue_stage(step);
     }
-    __syncthreads();
 
     // ---------------------------------------------------------------------- compute
     // Each lane works on PAIRS of redshifts (z, z+32) of the chunk for one target at a time:
@@ -177,14 +165,7 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
     for (int t = t_begin; t < t_end; ++t, ++it) {
         const int s = it % FSTAGES;
         const uint32_t ph = (it / FSTAGES) & 1;
-#if DL_PRODUCER == 1
-        if (lane == 0) {
-            const int want = it + FPREF;
-            if (want < nsteps && atomicCAS(next_issue, want, want + 1) == want) issue_stage(want);
-        }
-#else
-        if (threadIdx.x == DL_PRODWARP * 32 && it + FPREF < nsteps) issue_stage(it + FPREF);
-#endif
+        if (threadIdx.x == 0 && it + FPREF < nsteps) issue_stage(it + FPREF);
         __syncwarp();
         mbar_wait(&full[s], ph);
         const double* st = stage + s * ROWS * FZC;
@@ -215,14 +196,7 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
             }
 #pragma unroll
             for (int o = 0; o < FTO; ++o) {
-#if DL_ABL & 1
-                double tcr[6 * NF + 6];          // ablation: constants without shared loads
-#pragma unroll
-                for (int q = 0; q < 6 * NF + 6; ++q) tcr[q] = 1.0 + 0.001 * (q + o);
-                const double* tc = tcr;
-#else
                 const double* tc = tcw + o * TCS;
-#endif
                 const double hc = tc[6 * NF + 0], ic = tc[6 * NF + 1];
                 double pOT[ZJ], pTT[ZJ], pOO[ZJ];
 #pragma unroll
@@ -284,11 +258,7 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
                 bool up = false;
 #pragma unroll
                 for (int c = 0; c < ZJ; ++c) up |= __double2hiint(sarg[c]) > 0;
-#if DL_ABL & 2
-                if (false) {
-#else
                 if (__any_sync(0xffffffffu, up)) {
-#endif
                     // rare: the warp met a better cell than its reference exponent
                     double xl = x[0];
 #pragma unroll
@@ -316,11 +286,7 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
 #pragma unroll
                 for (int c = 0; c < ZJ; ++c)
                     up |= __double_as_longlong(v[c]) > __double_as_longlong(V);
-#if DL_ABL & 2
-                if (false) {
-#else
                 if (__any_sync(0xffffffffu, up)) {
-#endif
                     double vl = v[0];
 #pragma unroll
                     for (int c = 1; c < ZJ; ++c) vl = fmax(vl, v[c]);
@@ -333,9 +299,7 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
 #pragma unroll
                 for (int c = 0; c < ZJ; ++c) {
                     const double vp = v[c] * pr[c];
-#if !(DL_ABL & 4)
                     pdfw[o * FZC + zl + 32 * c] += vp;
-#endif
                     E[o] = fma(vp, wzv[c], E[o]);
                 }
             }
@@ -672,6 +636,74 @@ __global__ void zaux_kernel(int nz, int nzp, const double* __restrict__ zgrid,
     }
 }
 
+// CIlevel (delight/utils.py:196-205) for up to 8 fractions at once; one warp per target.
+//   evidence = trapz(PDF, grid)
+//   for level in linspace(0, PDF.max(), 200):  first level with
+//       trapz(PDF[PDF <= level], grid[PDF <= level]) >= fraction * evidence
+// The trapezoid over the compressed subset bridges the gaps between selected points, so each
+// selected point needs its previous selected point: found with a ballot inside a 32-point
+// chunk and carried between chunks.  Levels are scanned once for all fractions.
+constexpr int CI_MAXF = 8;
+__global__ void ci_levels_kernel(int nO, int nz, const double* __restrict__ pdf, long long ld,
+                                 const double* __restrict__ zgrid, int nfrac,
+                                 const double* __restrict__ fractions, int numlevels,
+                                 double* __restrict__ out) {
+    const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (o >= nO) return;
+    const double* p = pdf + (size_t)o * ld;
+    // evidence and max
+    double ev = 0.0, mx = -INFINITY;
+    for (int i = lane; i < nz; i += 32) {
+        mx = fmax(mx, p[i]);
+        if (i + 1 < nz) ev += (zgrid[i + 1] - zgrid[i]) * (p[i + 1] + p[i]) * 0.5;
+    }
+    ev = warp_sum(ev);
+    mx = warp_max(mx);
+    const double step = (mx - 0.0) / (double)(numlevels - 1);      // np.linspace
+    unsigned done = 0;
+    double res[CI_MAXF];
+#pragma unroll
+    for (int k = 0; k < CI_MAXF; ++k) res[k] = nan("");
+    const unsigned allmask = (1u << nfrac) - 1u;
+    for (int lv = 0; lv < numlevels && done != allmask; ++lv) {
+        const double level = (lv == numlevels - 1) ? mx : lv * step + 0.0;
+        double acc = 0.0, cz = 0.0, cp = 0.0;      // carried previous selected point
+        bool have = false;
+        for (int base = 0; base < nz; base += 32) {
+            const int i = base + lane;
+            const double y = i < nz ? p[i] : 0.0;
+            const double x = i < nz ? zgrid[i] : 0.0;
+            const bool sel = i < nz && y <= level;
+            const unsigned bal = __ballot_sync(0xffffffffu, sel);
+            const unsigned below = bal & ((1u << lane) - 1u);
+            const int src = below ? 31 - __clz(below) : 0;
+            const double px = __shfl_sync(0xffffffffu, x, src);
+            const double py = __shfl_sync(0xffffffffu, y, src);
+            if (sel) {
+                if (below) acc += (x - px) * (y + py) * 0.5;
+                else if (have) acc += (x - cz) * (y + cp) * 0.5;
+            }
+            if (bal) {
+                const int last = 31 - __clz(bal);
+                cz = __shfl_sync(0xffffffffu, x, last);
+                cp = __shfl_sync(0xffffffffu, y, last);
+                have = true;
+            }
+        }
+        acc = warp_sum(acc);
+#pragma unroll
+        for (int k = 0; k < CI_MAXF; ++k) {
+            if (k < nfrac && !(done & (1u << k)) && acc >= fractions[k] * ev) {
+                res[k] = level;
+                done |= 1u << k;
+            }
+        }
+    }
+    if (lane == 0)
+        for (int k = 0; k < nfrac; ++k) out[(size_t)o * nfrac + k] = res[k];
+}
+
 // prior[t][z] = exp(-0.5 ((z - z_t) / sigma)^2)   (scripts/delight-apply.py:104), padded rows
 __global__ void zprior_kernel(int nT, int nz, int nzp, const double* __restrict__ zgrid,
                               const double* __restrict__ ztrain, double sigma,
@@ -741,7 +773,7 @@ static int launch_fused_t(const FusedParams& p, cudaStream_t stream) {
     constexpr int ROWS = 2 * NF + 1;
     constexpr int TCS = tc_stride(NF);
     const size_t smem = sizeof(double) * (FSTAGES * ROWS * FZC + FTPC * FZC + FTPC * TCS + FTPC * 2 + FZC +
-                                          (ZDEP ? 4 * FZC : 0)) + 2 * FSTAGES * sizeof(uint64_t) + 16;
+                                          (ZDEP ? 4 * FZC : 0)) + 2 * FSTAGES * sizeof(uint64_t);
     auto kern = fused_like_kernel<NF, ZDEP>;
     DL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
@@ -933,6 +965,20 @@ int dl_metrics_dev(long long nO, long long nz, const double* pdf, long long ld_p
     DL_REQUIRE(nO > 0 && nz > 1 && ld_pdf >= nz, "bad shape");
     metrics_kernel<<<(unsigned)((nO + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
         (int)nO, (int)nz, pdf, ld_pdf, zgrid, ztrue, out);
+    DL_CUDA_CHECK(cudaGetLastError());
+    dl_count_launch();
+    return DL_OK;
+}
+
+// CIlevel for nfrac <= 8 fractions (device array); out [nO][nfrac].  NaN where the reference
+// would return None (never for fractions <= 1).
+int dl_ci_levels_dev(long long nO, long long nz, const double* pdf, long long ld_pdf,
+                     const double* zgrid, int nfrac, const double* fractions, int numlevels,
+                     double* out, void* stream) {
+    DL_REQUIRE(nO > 0 && nz > 1 && ld_pdf >= nz, "bad shape");
+    DL_REQUIRE(nfrac >= 1 && nfrac <= CI_MAXF && numlevels >= 2, "1..8 fractions");
+    ci_levels_kernel<<<(unsigned)((nO + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+        (int)nO, (int)nz, pdf, ld_pdf, zgrid, nfrac, fractions, numlevels, out);
     DL_CUDA_CHECK(cudaGetLastError());
     dl_count_launch();
     return DL_OK;

@@ -154,6 +154,13 @@ int dl_like_fused_dev(long long nO, long long nT, long long nz, long long nB, in
 int dl_metrics_dev(long long nO, long long nz, const double* pdf, long long ld_pdf,
                    const double* zgrid, const double* ztrue, double* out, void* stream);
 
+/* CIlevel                               replaces delight/utils.py:196-205 for nfrac <= 8
+ * fractions at once (computeMetrics passes 1 - confidenceLevels, utils.py:223-225).
+ * fractions: device array [nfrac]; numlevels = 200 in the reference; out [nO][nfrac]. */
+int dl_ci_levels_dev(long long nO, long long nz, const double* pdf, long long ld_pdf,
+                     const double* zgrid, int nfrac, const double* fractions, int numlevels,
+                     double* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Batched per-training-galaxy GP (device pointers).  Model = kernel grids from
  * dl_kernel_grids_dev on zGP (redshiftGridGP) / fzGrid (= 1 + zGP), template flux tables

@@ -235,12 +235,15 @@ def test_fused_golden_pipeline(sdss):
     assert len(list(t.groups())) >= 3
     res = apply.apply_fused(grid, prior, g["zgrid"], t, ell_hat=1.0,
                             ell_var=float(g["ellPriorSigma"]) ** 2, K=K, want_evid=True,
-                            want_metrics=True)
+                            want_metrics=True, confidence_levels=g["confidenceLevels"])
     ref = dict(pdf=g["pdfs"], evid=g["evid"], top_idx=g["top_idx"], top_ev=g["top_ev"])
     _check_fused(res, ref, K)
-    # metrics: first seven columns of computeMetrics + exact argmax index (zMAP)
-    np.testing.assert_allclose(res["metrics"][:, :7], g["metrics"][:, :7], rtol=1e-9)
-    np.testing.assert_array_equal(res["metrics"][:, 7].astype(int), g["pdfs"].argmax(axis=1))
+    # metrics: all 7 + nCL columns of computeMetrics (incl. the 200-level CIlevel scan) and the
+    # exact argmax index (zMAP)
+    ncol = g["metrics"].shape[1]
+    assert res["metrics"].shape[1] == ncol + 1
+    np.testing.assert_allclose(res["metrics"][:, :ncol], g["metrics"], rtol=1e-9)
+    np.testing.assert_array_equal(res["metrics"][:, ncol].astype(int), g["pdfs"].argmax(axis=1))
     # and the explicit-prior entry point gives the same thing
     prior2 = grid.explicit_prior(g["prior"])
     res2 = apply.apply_fused(grid, prior2, g["zgrid"], t, ell_hat=1.0,
