@@ -227,6 +227,76 @@ def cpu_baseline_sample(data, model_mean, model_covar, zt, budget_s=20.0):
                       "%.1f s" % (n, nz, nT, nB, dt)}
 
 
+def other_configs(data):
+    """Secondary BASELINE.json configurations, timed once each (CUDA events, inputs resident):
+    config 2 (templateFitting-equivalent, 100k targets x 8 templates x 1500 z x 5 bands) and
+    config 4 (delight-learn on 100k training galaxies, 28 bands with 2..21 valid per galaxy)."""
+    import torch
+    from delight_b200 import apply, gp as gpmod
+    out = {}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # ---- config 2
+    zgrid, tmpl = data["zgrid"], data["tmpl"][:, :5]
+    nt, nB, nz = tmpl.shape
+    f_mod = np.ascontiguousarray(tmpl.transpose(2, 0, 1))
+    b2 = data["p_z_t"] ** 2
+    p_z = data["p_t"][None, :] * zgrid[:, None] / b2[None, :] * np.exp(
+        -0.5 * zgrid[:, None] ** 2 / b2[None, :])                    # templateFitting.py:79-82
+    grid = apply.ModelGrid.from_legacy(f_mod, np.zeros_like(f_mod))
+    prior = grid.explicit_prior(p_z)
+    rng = np.random.default_rng(3)
+    nO = 100000
+    fl = f_mod[rng.integers(0, nz, nO), rng.integers(0, nt, nO)] * rng.uniform(.5, 2, (nO, 1))
+    fl = fl * (1 + 0.05 * rng.standard_normal(fl.shape))
+    tg = apply.Targets.full(fl, (0.05 * fl) ** 2).to_device()
+    ws = apply.FusedWorkspace()
+    run = lambda: apply.apply_fused(grid, prior, zgrid, tg, ell_hat=1.0, ell_var=1e24, K=0,
+                                    want_metrics=True, workspace=ws, out_device=True)
+    run()
+    ev0.record(); run(); ev1.record(); torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    out["c2_templatefit"] = {"workload": "100k targets x 8 CWW templates x 1500 z x 5 bands, "
+                             "PDF + metrics", "galaxies_per_s": nO / (ms * 1e-3), "ms": ms}
+    del grid, prior, tg
+    # ---- config 4
+    rng = np.random.default_rng(4)
+    nB, NC, nzg, nT = 28, 7, 150, 100000
+    mu0 = np.linspace(3500, 22000, nB)
+    amp = rng.uniform(0.2, 1.0, (nB, NC))
+    mu = mu0[:, None] + np.linspace(-300, 300, NC)[None, :]
+    sig = rng.uniform(80, 200, (nB, NC))
+    zgp = data["zgridGP"]
+    tm = 1e-6 * rng.uniform(0.5, 2.0, (8, nB, 1)) * (1 + 0.5 * np.sin(
+        zgrid[None, None, :] * rng.uniform(1, 5, (8, nB, 1))))
+    ev0.record()
+    gpm = gpmod.PhotozGPBatched(tm, zgrid, amp, mu, sig, [6500.0, 5002.26, 3732.22], 0.5, 0.5,
+                                1e3, 1e2, zgp)
+    ev1.record(); torch.cuda.synchronize()
+    grid_ms = ev0.elapsed_time(ev1)
+    z = rng.uniform(0.05, 2.9, nT)
+    nb = rng.integers(2, 22, nT)
+    order = np.argsort(rng.random((nT, nB)), axis=1)
+    keep = np.arange(nB)[None, :] < nb[:, None]
+    bands = np.sort(np.where(keep, order, nB + 1), axis=1)
+    bands = np.where(bands > nB, 0, bands)
+    ty = rng.integers(0, 8, nT)
+    iz = np.clip(((z - zgrid[0]) / (zgrid[1] - zgrid[0])).astype(int), 0, nz - 1)
+    true = 1e6 * tm[ty[:, None], bands, iz[:, None]]
+    fl = np.where(keep, true * (1 + 0.05 * rng.standard_normal(true.shape)), 0.0)
+    fv = np.where(keep, (0.05 * true) ** 2, 0.0)
+    cat = gpmod.catalogue(fl, fv, bands, nb, z)
+    gpm.fit(cat, out_device=True)
+    t0 = time.perf_counter(); rows = gpm.fit(cat, out_device=True); torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    ok = bool(torch.isfinite(rows).all().item())
+    out["c4_learn"] = {"workload": "100k training galaxies, 28 bands (2..21 valid each), "
+                       "template fit + K(X) + Cholesky + gpparams row; incl. H2D of the "
+                       "catalogue", "galaxies_per_s": nT / dt, "ms": dt * 1e3,
+                       "kernel_grid_28_bands_ms": grid_ms, "kernel_grid_pairs": nB * nB * nzg * nzg,
+                       "finite": ok}
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -344,6 +414,9 @@ def run_b200(args):
     h2d = h_flux.numel() * 8 + h_var.numel() * 8
     d2h = h_pdf.numel() * 8 + h_idx.numel() * 8 + h_ev.numel() * 8
 
+    extras = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras = other_configs(data)
     if rank == 0:
         peaks = measured_peaks()
         fp64 = ctypes.c_double(0)
@@ -393,6 +466,7 @@ def run_b200(args):
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "other_configs": extras,
         }
         print(json.dumps(line))
     if world > 1:
@@ -410,6 +484,7 @@ def main():
     ap.add_argument("--ref-targets", type=int, default=8,
                     help="reference arm: targets per step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary configurations")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -210,6 +210,16 @@ def apply_fused(grid, prior, zgrid, targets, ell_hat=1.0, ell_var=1.0, K=0, want
         raise ValueError("target band index outside the model grid")
     if K > nT:
         raise ValueError("Ncompress (K=%d) exceeds the number of training galaxies (%d)" % (K, nT))
+    if nO == 0:                     # empty catalogue slice (e.g. more ranks than targets)
+        empty = lambda *shape, dt=torch.float64: torch.empty(shape, dtype=dt, device="cuda")
+        out = dict(pdf=empty(0, nz), top_idx=empty(0, K, dt=torch.int64) if K else None,
+                   top_ev=empty(0, K) if K else None, evid=empty(0, nT) if want_evid else None,
+                   metrics=empty(0, 8 + (len(confidence_levels) if confidence_levels is not None
+                                         else 0)) if want_metrics else None, fused_launches=0)
+        if not out_device:
+            out = {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v)
+                   for k, v in out.items()}
+        return out
     ws = workspace or FusedWorkspace()
     zg = _as_dev(zgrid)
     zdep = np.ndim(ell_hat) > 0 or np.ndim(ell_var) > 0

@@ -579,3 +579,34 @@ def test_templatefit_config2_scale_properties():
     # noiseless targets: the posterior mode sits on the source redshift unless the p(z,t) prior
     # or a template degeneracy moves it
     assert (np.abs(res["metrics"][:, 7] - zi) <= 1).mean() > 0.5
+
+
+def test_fused_edge_cases(orc):
+    """Smallest legal shapes, an empty target slice, K = 0 and K = nT, a single band."""
+    from delight_b200 import apply
+    rng = np.random.default_rng(2)
+    for nO, nT, nz, nB, K in [(1, 1, 2, 1, 1), (2, 3, 5, 2, 3), (33, 2, 129, 3, 0)]:
+        zgrid = np.linspace(0.1, 1.0, nz)
+        mm = rng.uniform(1, 2, (nz, nT, nB))
+        mc = rng.uniform(.01, .02, (nz, nT, nB))
+        zt = rng.uniform(0.1, 1.0, nT)
+        fl = rng.uniform(1, 2, (nO, nB))
+        fv = rng.uniform(.01, .02, (nO, nB))
+        bands = np.tile(np.arange(nB), (nO, 1))
+        nfs = np.full(nO, nB)
+        ref = orc.apply_fused(fl, fv, nfs, bands, mm, mc, orc.z_prior(zgrid, zt, 0.5), zgrid,
+                              np.ones(nz), np.full(nz, 0.25), K, want_evid=True)
+        grid = apply.ModelGrid.from_legacy(mm, mc)
+        res = apply.apply_fused(grid, grid.gaussian_prior(zgrid, zt, 0.5), zgrid,
+                                apply.Targets(fl, fv, bands, nfs), ell_var=0.25, K=K,
+                                want_evid=True)
+        _check_fused(res, ref, K)
+        if K == 0:
+            assert res["top_idx"] is None
+        empty = apply.apply_fused(grid, grid.gaussian_prior(zgrid, zt, 0.5), zgrid,
+                                  apply.Targets(fl[:0], fv[:0], bands[:0], nfs[:0]), K=K,
+                                  want_metrics=True)
+        assert empty["pdf"].shape == (0, nz) and empty["fused_launches"] == 0
+    with pytest.raises(ValueError):
+        apply.apply_fused(grid, grid.gaussian_prior(zgrid, zt, 0.5), zgrid,
+                          apply.Targets(fl, fv, bands, nfs), K=nT + 1)
