@@ -124,8 +124,11 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
     // ---------------------------------------------------------------------- TMA producer
     // No dedicated producer warp (it would cost 32 registers/thread of occupancy): lane 0 of
     // warp 0 refills, before it computes step `it`, the stage every warp released FPREF steps
-    // ago.  (Measured alternatives: "first warp to arrive claims the refill" 2.8x slower -- the
-    // claimant sleeps in try_wait on the empty barrier; deeper rings 3-6 % slower.)
+    // ago.  (Measured alternatives, round 1: "first warp to arrive claims the refill"
+    // and "the producer role rotates over the warps" are both 2.8x slower; deeper rings 3-6 %
+    // slower; a 2-D tensor-map copy of all 2 NF rows (UTMALDG) instead of 2 NF bulk copies cuts
+    // the producer's issue time from 8 % to 2 % of warp 0 and the other warps' wait on it from
+    // 9 % to 3 %, but the resulting kernel was 14 % slower at full size -- not adopted.)
     const int nsteps = t_end - t_begin;
     auto issue_stage = [&](int step) {
         const int s = step % FSTAGES;
