@@ -149,7 +149,8 @@ def _as_dev(a):
 
 
 def _pick_nsplit(n_targets, nchunk, nT, sm_count):
-    ctas = nchunk * ((n_targets + 31) // 32)
+    tpc = _lib.lib().dl_fused_targets_per_cta()
+    ctas = nchunk * ((n_targets + tpc - 1) // tpc)
     want = 2 * sm_count          # 2 resident CTAs per SM
     if ctas >= want:
         return 1
@@ -185,9 +186,10 @@ class FusedWorkspace:
 
     def tile_size(self, nO, nT, nz, nsplit_hint=1):
         L = _lib.lib()
-        per32 = L.dl_fused_workspace_bytes(32, nT, nz, nsplit_hint, 0)
-        tile = max(32, (self.max_bytes // max(per32, 1)) * 32)
-        return int(min(tile, (nO + 31) // 32 * 32))
+        tpc = L.dl_fused_targets_per_cta()
+        per = L.dl_fused_workspace_bytes(tpc, nT, nz, nsplit_hint, 0)
+        tile = max(tpc, (self.max_bytes // max(per, 1)) * tpc)
+        return int(min(tile, (nO + tpc - 1) // tpc * tpc))
 
 
 def apply_fused(grid, prior, zgrid, targets, ell_hat=1.0, ell_var=1.0, K=0, want_evid=False,

@@ -29,6 +29,10 @@
 // computed.  All variances are pre-scaled by a per-target power of two c (exact) so products
 // over bands stay in range.
 #include "common.cuh"
+#ifdef DL_DBGWAIT
+#include <cstdio>
+#include <vector>
+#endif
 
 namespace dl {
 
@@ -54,7 +58,16 @@ constexpr int ZJ = DL_ZJ;         // redshifts a lane processes jointly (indepen
 constexpr int FZC = 32 * FZT;     // redshifts per CTA chunk
 constexpr int FSTAGES = DL_STAGES;  // TMA ring depth
 constexpr int FPREF = FSTAGES - 2;  // prefetch distance in steps
-constexpr int FTPC = FW * FTO;    // targets per CTA
+// Warp 0 also issues the TMA copies of every stage (6.5 % of its time, measured with
+// -DDL_DBGWAIT), which makes it the straggler the other seven warps wait for (~8 % of their
+// time; they free issue slots while they wait, so the net loss is ~3 %).  DL_ASYM=1 gives the
+// warp DL_LIGHTWARP one target less; measured round 1: lightening warp 0 or warp 4 (same
+// scheduler as warp 0) makes the kernel 1.8-2x SLOWER (warp 0 is then starved: the others wait
+// 60 % of the time for it, results identical), lightening warp 7 costs 9 %.  Default: off.
+#ifndef DL_ASYM
+#define DL_ASYM 0
+#endif
+constexpr int FTPC = FW * FTO - DL_ASYM;    // targets per CTA
 constexpr int FTHREADS = FW * 32;
 constexpr int MAXNF = 8;
 
@@ -73,6 +86,7 @@ struct FusedParams {
     double* Vw;            // [nsplit][nchunk][nO]
     int bands[MAXNF];
     int nB, nz, nzp, nT, nO, nchunk, nsplit;
+    long long* dbg;        // DL_DBGWAIT builds: [grid][FW][4] cycle counters
 };
 
 template <int NF, bool ZDEP>
@@ -130,11 +144,22 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
     // the producer's issue time from 8 % to 2 % of warp 0 and the other warps' wait on it from
     // 9 % to 3 %, but the resulting kernel was 14 % slower at full size -- not adopted.)
     const int nsteps = t_end - t_begin;
+#ifdef DL_DBGWAIT
+    long long dbg_empty = 0, dbg_issue = 0, dbg_wait = 0;
+    const long long dbg_t0 = clock64();
+#endif
     auto issue_stage = [&](int step) {
         const int s = step % FSTAGES;
         const uint32_t ph = (step / FSTAGES) & 1;
         const size_t row = (size_t)p.nzp;
+#ifdef DL_DBGWAIT
+        const long long ta = clock64();
+#endif
         mbar_wait(&empty[s], ph ^ 1);
+#ifdef DL_DBGWAIT
+        const long long tb = clock64();
+        dbg_empty += tb - ta;
+#endif
         mbar_arrive_expect_tx(&full[s], ROWS * FZC * sizeof(double));
         const double* gt = p.grid + (size_t)(t_begin + step) * 2 * p.nB * row + z0;
         double* dst = stage + s * ROWS * FZC;
@@ -147,6 +172,9 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
         }
         tma_bulk_g2s(dst + 2 * NF * FZC, p.prior + (size_t)(t_begin + step) * row + z0,
                      FZC * sizeof(double), &full[s]);
+#ifdef DL_DBGWAIT
+        dbg_issue += clock64() - tb;
+#endif
     };
     if (threadIdx.x == 0) {
         for (int step = 0; step < FPREF && step < nsteps; ++step) issue_stage(step);
@@ -159,10 +187,16 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
     double E[FTO];
 #pragma unroll
     for (int o = 0; o < FTO; ++o) E[o] = 0.0;
-    const double* tcw = tc_sm + warp * FTO * TCS;
-    double* pdfw = pdf_sm + warp * FTO * FZC;
-    double* rvw = rv_sm + warp * FTO * 2;
-    const int og0 = otile * FTPC + warp * FTO;
+    // targets of this warp: warp 0 owns FTO - DL_ASYM, the others FTO (contiguous in the tile)
+#ifndef DL_LIGHTWARP
+#define DL_LIGHTWARP 0
+#endif
+    const int nto = warp == DL_LIGHTWARP ? FTO - DL_ASYM : FTO;
+    const int tfirst = warp <= DL_LIGHTWARP ? warp * FTO : warp * FTO - DL_ASYM;
+    const double* tcw = tc_sm + tfirst * TCS;
+    double* pdfw = pdf_sm + tfirst * FZC;
+    double* rvw = rv_sm + tfirst * 2;
+    const int og0 = otile * FTPC + tfirst;
 
     int it = 0;
     for (int t = t_begin; t < t_end; ++t, ++it) {
@@ -170,7 +204,13 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
         const uint32_t ph = (it / FSTAGES) & 1;
         if (threadIdx.x == 0 && it + FPREF < nsteps) issue_stage(it + FPREF);
         __syncwarp();
+#ifdef DL_DBGWAIT
+        const long long tw0 = clock64();
         mbar_wait(&full[s], ph);
+        dbg_wait += clock64() - tw0;
+#else
+        mbar_wait(&full[s], ph);
+#endif
         const double* st = stage + s * ROWS * FZC;
 #pragma unroll 1
         for (int grp = 0; grp < FZT / ZJ; ++grp) {
@@ -199,6 +239,7 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
             }
 #pragma unroll
             for (int o = 0; o < FTO; ++o) {
+                if (DL_ASYM && o == FTO - 1 && nto < FTO) continue;     // warp-uniform
                 const double* tc = tcw + o * TCS;
                 const double hc = tc[6 * NF + 0], ic = tc[6 * NF + 1];
                 double pOT[ZJ], pTT[ZJ], pOO[ZJ];
@@ -315,7 +356,7 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
 #pragma unroll
             for (int o = 1; o < FTO; ++o) if (lane == o) ev = E[o];
             const int og = og0 + lane;
-            if (lane < FTO && og < p.nO)
+            if (lane < nto && og < p.nO)
                 p.evid_part[((size_t)chunk * p.nO + og) * p.nT + t] =
                     make_double2(ev, rvw[2 * lane]);
         }
@@ -325,10 +366,16 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
         if (lane == 0) mbar_arrive(&empty[s]);
     }
 
+#ifdef DL_DBGWAIT
+    if (p.dbg && lane == 0) {
+        long long* d = p.dbg + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * FW + warp) * 4;
+        d[0] = dbg_wait; d[1] = clock64() - dbg_t0; d[2] = dbg_empty; d[3] = dbg_issue;
+    }
+#endif
 #pragma unroll
     for (int o = 0; o < FTO; ++o) {
         const int og = og0 + o;
-        if (og < p.nO) {
+        if (o < nto && og < p.nO) {
             double* dst = p.pdf_part + ((size_t)split * p.nO + og) * p.nzp + z0;
 #pragma unroll
             for (int zj = 0; zj < FZT; ++zj) dst[zj * 32 + lane] = pdfw[o * FZC + zj * 32 + lane];
@@ -932,6 +979,17 @@ int dl_like_fused_dev(long long nO, long long nT, long long nz, long long nB, in
     }
     p.nB = (int)nB; p.nz = (int)nz; p.nzp = nzp; p.nT = (int)nT; p.nO = (int)nO;
     p.nchunk = nchunk; p.nsplit = nsplit;
+    p.dbg = nullptr;
+#ifdef DL_DBGWAIT
+    const size_t dbg_nb = (size_t)nchunk * ((nO + FTPC - 1) / FTPC) * nsplit;
+    {
+        static long long* dbg = nullptr;
+        if (dbg) cudaFree(dbg);
+        cudaMalloc(&dbg, dbg_nb * FW * 4 * 8);
+        cudaMemset(dbg, 0, dbg_nb * FW * 4 * 8);
+        p.dbg = dbg;
+    }
+#endif
     int rc = zdep ? launch_fused_nf<true>(nf, p, stream) : launch_fused_nf<false>(nf, p, stream);
     if (rc != DL_OK) return rc;
 
@@ -953,6 +1011,23 @@ int dl_like_fused_dev(long long nO, long long nT, long long nz, long long nB, in
         DL_CUDA_CHECK(cudaGetLastError());
         dl_count_launch();
     }
+#ifdef DL_DBGWAIT
+    {
+        std::vector<long long> h(dbg_nb * FW * 4);
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h.data(), p.dbg, h.size() * 8, cudaMemcpyDeviceToHost);
+        double w[FW] = {0}, tt[FW] = {0}, em = 0, is = 0;
+        for (size_t b = 0; b < dbg_nb; ++b)
+            for (int q = 0; q < FW; ++q) {
+                w[q] += h[(b * FW + q) * 4]; tt[q] += h[(b * FW + q) * 4 + 1];
+                if (q == 0) { em += h[(b * FW) * 4 + 2]; is += h[(b * FW) * 4 + 3]; }
+            }
+        fprintf(stderr, "[dbgwait] fraction of warp time waiting on TMA data:");
+        for (int q = 0; q < FW; ++q) fprintf(stderr, " w%d=%.3f", q, w[q] / tt[q]);
+        fprintf(stderr, " | producer: empty-wait %.3f issue %.3f | CTA lifetime %.3g cyc\n",
+                em / tt[0], is / tt[0], tt[0] / dbg_nb);
+    }
+#endif
     if (K > 0) {
         DL_REQUIRE(top_idx && top_ev, "top-K outputs missing");
         topk_kernel<<<(unsigned)nO, TK_THREADS, 0, stream>>>((int)nT, K, evid_int, top_idx,
