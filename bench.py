@@ -34,6 +34,11 @@ N_COMPRESS = 50
 ELL_VAR = 0.25            # ellPriorSigma 0.5 (tests/parametersTest.cfg:57)
 Z_PRIOR_SIGMA = 0.5
 FLOP_PER_CELL = lambda nf: 27 * nf + 30     # SURVEY.md 8(d), fused path
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE fused_like_kernel launch at the default
+# configuration, from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` on a B200
+# (profiles/r1_fused_like_dram_traffic.csv): 6.94 GB read (1.6 GB grid + prior, re-read once per
+# CTA wave) + 19.37 GB written (per-z-chunk evidence partials, 12 x 16 B per (target, training)).
+NCU_TRAFFIC_BYTES_DEFAULT_CONFIG = 6937007104 + 19368152064
 
 
 def workload_name(nO, nT, nz, nB):
@@ -433,9 +438,11 @@ def run_b200(args):
                            "MEASURED_PEAKS.json has no FP64 entry; datasheet 37.2 TFLOP/s",
             "flop_per_cell": FLOP_PER_CELL(nB), "cells_per_launch": cells_per_launch,
             "kernel_ms": k_ms, "kernel_share_of_step": kms.value / ms_total,
-            "traffic": None,
-            "hbm_algorithmic_GBs": grid_bytes * (kn.value / args.steps) / (ms_total / args.steps
-                                                                          * 1e-3) * 1e-9,
+            "traffic": (NCU_TRAFFIC_BYTES_DEFAULT_CONFIG
+                        if (nO, nT) == (N_TARGETS, N_TRAIN) else None),
+            "traffic_unit": "bytes per launch (ncu dram read+write, profiles/)",
+            "hbm_algorithmic_bytes_per_launch": grid_bytes + nO * (2 * nB * 8 + nz * 8
+                                                                  + N_COMPRESS * 16 + 64),
             "hbm_peak_GBs": peaks.get("hbm_gbs"),
         }
         cpu = None
