@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _lib
 
-FUSED_MAX_BANDS = 8
+FUSED_MAX_BANDS = 16
 
 
 def partition(n, rank, size):
@@ -39,6 +39,15 @@ class Targets:
             raise ValueError("Targets: fluxes, fluxes_var, bands must be [nO, nB]; nf [nO]")
         if self.nf.size and (self.nf.min() < 1 or self.nf.max() > self.fluxes.shape[1]):
             raise ValueError("Targets: nf must be in [1, nB]")
+        valid = np.arange(self.fluxes.shape[1])[None, :] < self.nf[:, None]
+        if not np.all(np.isfinite(self.fluxes[valid])) or \
+                not np.all(self.fluxes_var[valid] > 0) or \
+                not np.all(np.isfinite(self.fluxes_var[valid])):
+            # the catalogue reader drops such entries (io.py:331-337); the kernels assume it
+            raise ValueError("Targets: fluxes must be finite and variances finite and > 0 "
+                             "in the valid bands")
+        if np.any(self.bands[valid] < 0):
+            raise ValueError("Targets: negative band index in a valid slot")
 
     @classmethod
     def full(cls, fluxes, fluxes_var, ztrue=None):

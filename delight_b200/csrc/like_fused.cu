@@ -54,7 +54,8 @@ namespace dl {
 constexpr int FW = DL_FW;         // compute warps per CTA
 constexpr int FTO = DL_FTO;       // targets per compute warp
 constexpr int FZT = 4;            // redshifts per lane
-constexpr int ZJ = DL_ZJ;         // redshifts a lane processes jointly (independent chains)
+constexpr int ZJ_SMALL = DL_ZJ;   // redshifts a lane processes jointly (independent chains),
+constexpr int ZJ_LARGE = 1;       //   NF <= 8 / NF > 8 (register budget: 8 NF ZJ registers of model values)
 constexpr int FZC = 32 * FZT;     // redshifts per CTA chunk
 constexpr int FSTAGES = DL_STAGES;  // TMA ring depth
 constexpr int FPREF = FSTAGES - 2;  // prefetch distance in steps
@@ -69,7 +70,7 @@ constexpr int FPREF = FSTAGES - 2;  // prefetch distance in steps
 #endif
 constexpr int FTPC = FW * FTO - DL_ASYM;    // targets per CTA
 constexpr int FTHREADS = FW * 32;
-constexpr int MAXNF = 8;
+constexpr int MAXNF = 16;
 
 // per-target constants: [f][2] = (a', w') | [f][4] = (var', obs, obs^2, 0) | hc ic pOT pTT pOO c
 __host__ __device__ constexpr int tc_stride(int nf) { return 6 * nf + 6; }
@@ -89,7 +90,7 @@ struct FusedParams {
     long long* dbg;        // DL_DBGWAIT builds: [grid][FW][4] cycle counters
 };
 
-template <int NF, bool ZDEP>
+template <int NF, bool ZDEP, int ZJ>
 __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const FusedParams p) {
     constexpr int ROWS = 2 * NF + 1;
     constexpr int TCS = tc_stride(NF);
@@ -826,11 +827,12 @@ __global__ void relayout_prior_kernel(int nz, int nT, int nzp, const double* __r
 
 template <int NF, bool ZDEP>
 static int launch_fused_t(const FusedParams& p, cudaStream_t stream) {
+    constexpr int ZJ = NF <= 8 ? ZJ_SMALL : ZJ_LARGE;
     constexpr int ROWS = 2 * NF + 1;
     constexpr int TCS = tc_stride(NF);
     const size_t smem = sizeof(double) * (FSTAGES * ROWS * FZC + FTPC * FZC + FTPC * TCS + FTPC * 2 + FZC +
                                           (ZDEP ? 4 * FZC : 0)) + 2 * FSTAGES * sizeof(uint64_t);
-    auto kern = fused_like_kernel<NF, ZDEP>;
+    auto kern = fused_like_kernel<NF, ZDEP, ZJ>;
     DL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
     const int notile = (p.nO + FTPC - 1) / FTPC;
@@ -854,6 +856,14 @@ static int launch_fused_nf(int NF, const FusedParams& p, cudaStream_t stream) {
         case 6: return launch_fused_t<6, ZDEP>(p, stream);
         case 7: return launch_fused_t<7, ZDEP>(p, stream);
         case 8: return launch_fused_t<8, ZDEP>(p, stream);
+        case 9: return launch_fused_t<9, ZDEP>(p, stream);
+        case 10: return launch_fused_t<10, ZDEP>(p, stream);
+        case 11: return launch_fused_t<11, ZDEP>(p, stream);
+        case 12: return launch_fused_t<12, ZDEP>(p, stream);
+        case 13: return launch_fused_t<13, ZDEP>(p, stream);
+        case 14: return launch_fused_t<14, ZDEP>(p, stream);
+        case 15: return launch_fused_t<15, ZDEP>(p, stream);
+        case 16: return launch_fused_t<16, ZDEP>(p, stream);
     }
     dl_set_error("fused likelihood supports 1..%d bands per target group, got %d", MAXNF, NF);
     return DL_ERR_UNSUPPORTED;
@@ -942,7 +952,7 @@ int dl_like_fused_dev(long long nO, long long nT, long long nz, long long nB, in
                       long long workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     DL_REQUIRE(nO > 0 && nT > 0 && nz > 1 && nB > 0, "bad shape");
-    DL_REQUIRE(nf >= 1 && nf <= MAXNF, "1..8 bands per target group");
+    DL_REQUIRE(nf >= 1 && nf <= MAXNF, "1..16 bands per target group");
     DL_REQUIRE(nsplit >= 1 && nsplit <= nT, "bad nsplit");
     DL_REQUIRE(K >= 0 && K <= TK_MAXK && K <= nT, "0 <= K <= min(nT, 1024)");
     DL_REQUIRE(ld_pdf >= nz, "ld_pdf < nz");

@@ -137,7 +137,7 @@ int dl_zprior_dev(long long nT, long long nz, const double* zgrid, const double*
 
 /* Fused likelihood + apply epilogue   replaces scripts/delight-apply.py:137-162 x nO targets
  * (approx_flux_likelihood_cy, like*=prior, pdf=sum_t, evid=trapz_z, top-K) for one group of
- * targets that share the band list `bands` (HOST array, nf <= 8 entries).
+ * targets that share the band list `bands` (HOST array, nf <= 16 entries).
  *   obs/var [nO][nf]; ell_hat/ell_var scalars, or device vectors ell_hat_z/ell_var_z [nz]
  *   pdf [nO][ld_pdf] out; evid [nO][nT] out or NULL; top_idx [nO][K] / top_ev [nO][K] out
  *   (K = 0: skipped).  Ties: descending evidence, equal -> larger index first. */

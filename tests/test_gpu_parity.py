@@ -271,6 +271,8 @@ def test_fused_templatefit_golden(golden, sdss):
     (5, 40, 128, 8, 8, False, 1),
     (40, 64, 751, 5, 5, False, 2),
     (3, 33, 50, 4, 1, True, None),
+    (20, 60, 200, 16, 16, False, None),      # > 8 bands: single-redshift variant of the kernel
+    (9, 30, 129, 12, 11, True, 2),
 ])
 def test_fused_vs_oracle_random(orc, nO, nT, nz, nB, nf, zdep, nsplit):
     from delight_b200 import apply

@@ -60,6 +60,13 @@ def test_target_grouping_by_band_set():
     assert groups == {(0, 1, 2, 3, 4): [0, 2], (0, 1, 3, 4): [1], (1, 2): [3]}
     with pytest.raises(ValueError):
         apply.Targets(fl, fl, bands, np.array([5, 4, 5, 0]))
+    bad = fl.copy()
+    bad[1, 2] = 0.0                      # zero variance in a valid slot
+    with pytest.raises(ValueError):
+        apply.Targets(fl, bad, bands, nf)
+    bad[1, 2] = 1.0
+    bad[3, 4] = -7.0                     # garbage in an unused slot is fine
+    apply.Targets(fl, bad, bands, nf)
 
 
 def test_dropin_signatures_and_dtype_errors():
