@@ -432,6 +432,9 @@ def run_b200(args):
         grid_bytes = grid.grid.numel() * 8 + prior.numel() * 8
         roofline = {
             "bound": "fp64", "kernel": "fused_like_kernel<%d,false>" % nB,
+            "bound_note": "FP64 vector (FMA) pipe: no stage is a dense contraction (tensor cores "
+                          "not applicable) and HBM traffic is 3 orders of magnitude below its "
+                          "roofline (BASELINE.json metric: % of FP64/HBM roofline)",
             "achieved": achieved, "peak": fp64.value, "unit": "TFLOP/s",
             "frac": achieved / fp64.value if fp64.value else None,
             "peak_source": "measured live: dl_fp64_peak (dependent FMA chains, all SMs); "
