@@ -219,7 +219,11 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
         mbar_wait(&full[s], ph);
 #endif
         const double* st = stage + s * ROWS * FZC;
+#ifdef DL_NO_GRPUNROLL
 #pragma unroll 1
+#else
+#pragma unroll
+#endif
         for (int grp = 0; grp < FZT / ZJ; ++grp) {
             const int zl = grp * 32 * ZJ + lane;      // cells: zl + 32 c, c < ZJ
             double m[ZJ][NF], cv[ZJ][NF];
