@@ -1,0 +1,237 @@
+"""File-level drivers of the batched path: the same parameter file, catalogues and output files as
+scripts/delight-learn.py and scripts/delight-apply.py, with the per-galaxy Python loops replaced
+by the batched device calls of `gp` / `apply` and targets sharded over ranks (torchrun).
+
+    python -m delight_b200.pipeline learn  params.cfg
+    python -m delight_b200.pipeline apply  params.cfg
+    torchrun --nproc-per-node 8 -m delight_b200.pipeline apply params.cfg
+
+Host-side format code only (the numeric work is in libdelight_b200.so).  The readers restate the
+semantics of delight/io.py for the keys and columns this path uses:
+  * parameter file: the [Bands]/[Templates]/[Training]/[Target]/[Other] keys of io.py:12-190;
+  * catalogue rows: io.py:305-351 -- per object the valid bands are those with finite, positive
+    flux AND variance; objects with a bad reference flux, z < 0 (also: no redshift column) or
+    fewer than two valid bands are skipped; variance += (training_extraFracFluxError * flux)^2
+    for targets too (the reference uses the training key for both prefixes, io.py:350-351);
+  * gpparams rows: `%i` + `%.12e` columns (delight-learn.py:48,130);
+  * outputs: `%.2e` PDFs / metrics / evidences, `%i` indices (delight-apply.py:222-233).
+Rows of skipped objects stay zero at the END of the output arrays, as in the reference (its
+`loc` counter only advances on yielded objects).
+"""
+import configparser
+import os
+import sys
+
+import numpy as np
+
+from . import apply as _apply
+from . import distributed as _dist
+from . import gp as _gp
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter file (subset of delight/io.py:12-190 used by learn / apply)
+# ------------------------------------------------------------------------------------------------
+def parse_params(path):
+    cfg = configparser.ConfigParser()
+    if not os.path.isfile(path):
+        raise Exception(path + " : file not found")
+    cfg.read(path)
+    for sec in ("Bands", "Templates", "Training", "Target", "Other"):
+        if not cfg.has_section(sec):
+            raise Exception(sec + " not found in parameter file")
+    floats = lambda s: [float(x) for x in s.split(" ") if x]
+    p = {}
+    p["bands_directory"] = cfg.get("Bands", "directory")
+    p["bandNames"] = cfg.get("Bands", "Names").split(" ")
+    p["templates_directory"] = cfg.get("Templates", "directory")
+    p["templates_names"] = cfg.get("Templates", "names").split(" ")
+    p["p_t"] = np.array(floats(cfg.get("Templates", "p_t")))
+    p["p_z_t"] = np.array(floats(cfg.get("Templates", "p_z_t")))
+    for pre, sec in (("training_", "Training"), ("target_", "Target")):
+        p[pre + "catFile"] = cfg.get(sec, "catFile")
+        p[pre + "referenceBand"] = cfg.get(sec, "referenceBand")
+        p[pre + "bandOrder"] = cfg.get(sec, "bandOrder").split(" ")
+        p[pre + "extraFracFluxError"] = cfg.getfloat(sec, "extraFracFluxError")
+    p["training_paramFile"] = cfg.get("Training", "paramFile")
+    p["training_numChunks"] = cfg.getint("Training", "numChunks")
+    for k in ("compressIndicesFile", "compressMargLikFile", "redshiftpdfFile", "metricsFile"):
+        p[k] = cfg.get("Target", k)
+    p["Ncompress"] = cfg.getint("Target", "Ncompress")
+    p["useCompression"] = cfg.getboolean("Target", "useCompression")
+    p["compressionFilesFound"] = os.path.isfile(p["compressIndicesFile"]) and \
+        os.path.isfile(p["compressMargLikFile"])
+    for k in ("zPriorSigma", "ellPriorSigma", "alpha_C", "alpha_L", "V_C", "V_L", "redshiftMin",
+              "redshiftMax", "redshiftBinSize"):
+        p[k] = cfg.getfloat("Other", k)
+    p["redshiftNumBinsGPpred"] = cfg.getint("Other", "redshiftNumBinsGPpred")
+    p["lines_pos"] = floats(cfg.get("Other", "lines_pos"))
+    p["confidenceLevels"] = floats(cfg.get("Other", "confidenceLevels"))
+    return p
+
+
+def read_band_coefficients(p):
+    """io.readBandCoefficients (io.py:219-238)."""
+    amp, mu, sig = [], [], []
+    for band in p["bandNames"]:
+        d = np.loadtxt(os.path.join(p["bands_directory"], band + "_gaussian_coefficients.txt"))
+        amp.append(d[:, 0]); mu.append(d[:, 1]); sig.append(d[:, 2])
+    return np.vstack(amp), np.vstack(mu), np.vstack(sig)
+
+
+def create_grids(p):
+    """io.createGrids (io.py:241-260): fine linear grid, log-spaced GP grid."""
+    zgrid = np.arange(p["redshiftMin"], p["redshiftMax"], p["redshiftBinSize"])
+    zgp = np.logspace(np.log10(p["redshiftMin"]), np.log10(p["redshiftMax"] * 1.01),
+                      p["redshiftNumBinsGPpred"])
+    return zgrid, zgp
+
+
+def read_template_tables(p):
+    """The <sed>_fluxredshiftmod.txt tables behind io.readSEDs (io.py:263-277) -> [nt, nB, nz]."""
+    return np.stack([np.loadtxt(os.path.join(p["templates_directory"],
+                                             s + "_fluxredshiftmod.txt")).T
+                     for s in p["templates_names"]])
+
+
+def column_positions(p, prefix):
+    """io.readColumnPositions (io.py:193-216)."""
+    order = p[prefix + "bandOrder"]
+    band_idx = np.array([ib for ib, b in enumerate(p["bandNames"]) if b in order])
+    names = [p["bandNames"][i] for i in band_idx]
+    cols = np.array([order.index(b) for b in names])
+    vcols = np.array([order.index(b + "_var") for b in names])
+    zcol = order.index("redshift") if "redshift" in order else -1
+    refcol = order.index(p[prefix + "referenceBand"])
+    return band_idx, cols, vcols, zcol, refcol
+
+
+def read_catalogue(p, prefix, first=0, last=None):
+    """Catalogue rows [first, last) -> packed apply.Targets (io.py:305-351 semantics).
+    Returns (targets, n_lines) where n_lines counts file rows in the range."""
+    band_idx, cols, vcols, zcol, refcol = column_positions(p, prefix)
+    data = np.loadtxt(p[prefix + "catFile"], ndmin=2)[first:last]
+    n_lines = data.shape[0]
+    flux, var = data[:, cols], data[:, vcols]
+    mask = np.isfinite(flux) & np.isfinite(var) & (flux > 0.0) & (var > 0.0)
+    z = data[:, zcol] if zcol >= 0 else np.full(n_lines, -1.0)
+    ref = data[:, refcol]
+    keep = ~((ref <= 0) | ~np.isfinite(ref) | (z < 0) | (mask.sum(axis=1) <= 1))
+    flux, var, mask, z = flux[keep], var[keep], mask[keep], z[keep]
+    n, nb = flux.shape
+    nf = mask.sum(axis=1)
+    order = np.argsort(~mask, axis=1, kind="stable")          # valid bands first, in band order
+    take = lambda a: np.take_along_axis(a, order, axis=1)
+    valid = np.arange(nb)[None, :] < nf[:, None]
+    fl = np.where(valid, take(flux), 0.0)
+    fv = np.where(valid, take(var), 0.0)
+    fv = np.where(valid, fv + (p["training_extraFracFluxError"] * fl) ** 2, 0.0)
+    bands = np.where(valid, take(np.broadcast_to(band_idx, flux.shape)), 0)
+    # left-pack into nB-wide arrays (nB = bands of the model)
+    nB = len(p["bandNames"])
+    pad = lambda a, dt: np.concatenate([a, np.zeros((n, nB - nb), dtype=dt)], axis=1)
+    return _apply.Targets(pad(fl, float), pad(fv, float), pad(bands, np.int64), nf, z), n_lines
+
+
+def make_gp(p):
+    amp, mu, sig = read_band_coefficients(p)
+    zgrid, zgp = create_grids(p)
+    tmpl = read_template_tables(p)
+    gpm = _gp.PhotozGPBatched(tmpl, zgrid, amp, mu, sig, p["lines_pos"], p["V_C"], p["V_L"],
+                              p["alpha_C"], p["alpha_L"], zgp)
+    return gpm, zgrid
+
+
+# ------------------------------------------------------------------------------------------------
+# learn  (scripts/delight-learn.py)
+# ------------------------------------------------------------------------------------------------
+def learn(cfg_path, write=True):
+    p = parse_params(cfg_path)
+    rank, size = _dist.init()
+    gpm, _ = make_gp(p)
+    n_total = sum(1 for _ in open(p["training_catFile"]))
+    first, last = _dist.partition(n_total, rank, size)            # delight-learn.py:31-33
+    cat, n_lines = read_catalogue(p, "training_", first, last)
+    import torch
+    rows = torch.zeros((n_lines, gpm.numCol), dtype=torch.float64, device="cuda")
+    if len(cat):
+        rows[:len(cat)] = gpm.fit(cat, out_device=True)
+    rows = _dist.gather_rows(rows, n_total)                       # delight-learn.py:125
+    if rank == 0:
+        rows = rows.cpu().numpy()
+        if write:
+            fmt = "%i " + "%.12e " * (rows.shape[1] - 1)          # delight-learn.py:48
+            np.savetxt(p["training_paramFile"], rows, fmt=fmt)
+    return rows if rank == 0 else None
+
+
+# ------------------------------------------------------------------------------------------------
+# apply  (scripts/delight-apply.py)
+# ------------------------------------------------------------------------------------------------
+def apply(cfg_path, write=True, cap_training_like_reference=True):
+    """cap_training_like_reference: delight-apply.py:79-80 bounds the training rows it loads by
+    the number of TARGET objects (`TR_lastLine` uses numObjectsTarget); keep that for parity."""
+    p = parse_params(cfg_path)
+    if p["training_numChunks"] != 1:
+        raise NotImplementedError("numChunks > 1 normalises each chunk separately in the "
+                                  "reference (SURVEY appendix A); only numChunks = 1")
+    if p["useCompression"] and p["compressionFilesFound"]:
+        raise NotImplementedError("second (compressed) pass is not implemented")
+    rank, size = _dist.init()
+    import torch
+    gpm, zgrid = make_gp(p)
+    n_train = sum(1 for _ in open(p["training_paramFile"]))
+    n_target = sum(1 for _ in open(p["target_catFile"]))
+    tr_last = int(min(n_train, n_target)) if cap_training_like_reference else n_train
+    rows = np.loadtxt(p["training_paramFile"], ndmin=2)[:tr_last]
+    rows = rows[rows[:, 0] >= 1]                                   # unused (skipped) rows
+    ncol = gpm.numCol
+    if rows.shape[1] < ncol:
+        raise ValueError("gpparams file has too few columns for this band / template set")
+    grid, train_z = gpm.predict(np.ascontiguousarray(rows[:, :ncol]))
+    prior = grid.gaussian_prior(zgrid, train_z, p["zPriorSigma"])
+    first, last = _dist.partition(n_target, rank, size)           # delight-apply.py:50-53
+    targets, n_lines = read_catalogue(p, "target_", first, last)
+    K = p["Ncompress"]
+    ncl = len(p["confidenceLevels"])
+    with_z = "redshift" in p["target_bandOrder"]
+    res = _apply.apply_fused(grid, prior, zgrid, targets, ell_hat=1.0,
+                             ell_var=p["ellPriorSigma"] ** 2, K=K, want_metrics=with_z,
+                             confidence_levels=p["confidenceLevels"], out_device=True)
+
+    def full(a, width, dt=torch.float64):
+        out = torch.zeros((n_lines, width), dtype=dt, device="cuda")
+        if a is not None and a.shape[0]:
+            out[:a.shape[0]] = a[:, :width]
+        return out
+    pdfs = _dist.gather_rows(full(res["pdf"], zgrid.size), n_target)          # :201
+    idx = _dist.gather_rows(full(res["top_idx"], K, torch.int64), n_target)   # :206-210
+    ev = _dist.gather_rows(full(res["top_ev"], K), n_target)
+    if with_z and res["metrics"] is not None and res["metrics"].shape[0]:
+        # the reference only fills the metrics of objects whose PDF has mass (:164-166)
+        res["metrics"][res["pdf"].sum(dim=1) <= 0] = 0.0
+    met = _dist.gather_rows(full(res["metrics"], 7 + ncl), n_target) if with_z else None  # :216
+    if rank != 0:
+        return None
+    out = dict(pdfs=pdfs.cpu().numpy(), top_idx=idx.cpu().numpy(), top_ev=ev.cpu().numpy(),
+               metrics=met.cpu().numpy() if with_z else None)
+    if write:                                                      # delight-apply.py:222-233
+        np.savetxt(p["redshiftpdfFile"], out["pdfs"], fmt="%.2e")
+        if with_z:
+            np.savetxt(p["metricsFile"], out["metrics"], fmt="%.2e")
+        if p["useCompression"] and not p["compressionFilesFound"]:
+            np.savetxt(p["compressMargLikFile"], out["top_ev"], fmt="%.2e")
+            np.savetxt(p["compressIndicesFile"], out["top_idx"], fmt="%i")
+    return out
+
+
+def main(argv=None):
+    argv = sys.argv[1:] if argv is None else argv
+    if len(argv) != 2 or argv[0] not in ("learn", "apply"):
+        raise SystemExit("usage: python -m delight_b200.pipeline {learn|apply} params.cfg")
+    print("--- DELIGHT-%s (b200) ---" % argv[0].upper())
+    (learn if argv[0] == "learn" else apply)(argv[1])
+
+
+if __name__ == "__main__":
+    main()

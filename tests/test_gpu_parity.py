@@ -612,3 +612,32 @@ def test_fused_edge_cases(orc):
     with pytest.raises(ValueError):
         apply.apply_fused(grid, grid.gaussian_prior(zgrid, zt, 0.5), zgrid,
                           apply.Targets(fl, fv, bands, nfs), K=nT + 1)
+
+
+def test_batched_pipeline_same_files_as_reference(sdss, tmp_path):
+    """python -m delight_b200.pipeline learn/apply: same cfg, catalogues and output files as the
+    reference scripts, through the batched device path (one process, WORLD_SIZE = 1)."""
+    from oracle import pipeline as refpipe
+    from delight_b200 import pipeline
+    g = sdss
+    wd = str(tmp_path)
+    K = int(g["Ncompress"])
+    cfg = refpipe.make_workdir(wd, bands=refpipe.SDSS,
+                               train_bands=["U_SDSS", "G_SDSS", "I_SDSS"], refband="I_SDSS",
+                               numObjects=24, dz=0.01, nzGP=40, Ncompress=K, copy_data=False)
+    refpipe.write_preprocessed(wd, refpipe.SDSS, g["amp"], g["mu"], g["sig"], g["tmpl"])
+    np.savetxt(wd + "/galaxies-fluxredshifts.txt", g["train_cat"])
+    np.savetxt(wd + "/galaxies-fluxredshifts2.txt", g["target_cat"])
+    rows = pipeline.learn(cfg)
+    np.testing.assert_allclose(rows, g["gp_rows"], rtol=1e-9, atol=1e-11 * np.abs(g["gp_rows"]).max())
+    txt = np.loadtxt(wd + "/galaxies-gpparams.txt")
+    np.testing.assert_allclose(txt, g["gp_rows"], rtol=1e-9, atol=1e-11 * np.abs(g["gp_rows"]).max())
+    out = pipeline.apply(cfg)
+    n = g["pdfs"].shape[0]
+    np.testing.assert_allclose(out["pdfs"][:n], g["pdfs"], rtol=1e-6, atol=1e-290 * g["pdfs"].max())
+    assert np.all(out["pdfs"][n:] == 0)
+    np.testing.assert_array_equal(out["top_idx"][:n], g["top_idx"])
+    np.testing.assert_allclose(out["metrics"][:n], g["metrics"], rtol=1e-6)
+    pdfs = np.loadtxt(wd + "/redshiftpdfs.txt")
+    np.testing.assert_allclose(pdfs[:n], g["pdfs"], rtol=6e-3, atol=1e-300)
+    assert np.loadtxt(wd + "/compressIndices.txt", dtype=np.int64).shape == (pdfs.shape[0], K)

@@ -101,3 +101,30 @@ def test_product_never_references_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(root, f)).read()
                 assert "oracle" not in txt, os.path.join(root, f)
+
+
+def test_catalogue_reader_matches_reference_parsing(golden, tmp_path):
+    """pipeline.read_catalogue vs what the reference's io.getDataFromFile yielded for the same
+    rows (valid-band lists, variance inflation, skip rule)."""
+    from delight_b200 import pipeline
+    g = golden("sdss_pipeline")
+    wd = str(tmp_path)
+    np.savetxt(wd + "/tr.txt", g["train_cat"])
+    np.savetxt(wd + "/ta.txt", g["target_cat"])
+    names = ["U_SDSS", "G_SDSS", "R_SDSS", "I_SDSS", "Z_SDSS"]
+    p = dict(bandNames=names, training_catFile=wd + "/tr.txt", target_catFile=wd + "/ta.txt",
+             training_bandOrder=str(g["train_bandOrder"]).split(" "),
+             target_bandOrder=str(g["target_bandOrder"]).split(" "),
+             training_referenceBand="I_SDSS", target_referenceBand="I_SDSS",
+             training_extraFracFluxError=float(g["extraFrac"]))
+    for prefix, key in (("training_", "tr"), ("target_", "ta")):
+        cat, n_lines = pipeline.read_catalogue(p, prefix)
+        nb = g[key + "_nb"]
+        assert len(cat) == nb.size and n_lines >= nb.size
+        np.testing.assert_array_equal(cat.nf, nb)
+        np.testing.assert_array_equal(cat.ztrue, g[key + "_z"])
+        for i in range(nb.size):
+            B = nb[i]
+            np.testing.assert_array_equal(cat.bands[i, :B], g[key + "_bands"][i, :B])
+            np.testing.assert_array_equal(cat.fluxes[i, :B], g[key + "_flux"][i, :B])
+            np.testing.assert_allclose(cat.fluxes_var[i, :B], g[key + "_var"][i, :B], rtol=1e-15)
