@@ -641,3 +641,68 @@ def test_batched_pipeline_same_files_as_reference(sdss, tmp_path):
     pdfs = np.loadtxt(wd + "/redshiftpdfs.txt")
     np.testing.assert_allclose(pdfs[:n], g["pdfs"], rtol=6e-3, atol=1e-300)
     assert np.loadtxt(wd + "/compressIndices.txt", dtype=np.int64).shape == (pdfs.shape[0], K)
+
+
+# ------------------------------------------------------------------------------------------------
+# randomized shapes for the drop-in operators vs the oracle
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("NO1,NO2,nB,NC,NL", [(1, 1, 1, 1, 0), (17, 5, 3, 7, 3), (40, 33, 28, 15, 8),
+                                              (150, 150, 2, 7, 1)])
+def test_kernelparts_random_shapes(orc, NO1, NO2, nB, NC, NL):
+    from delight_b200.photoz_kernels_cy import kernelparts, kernelparts_diag
+    rng = np.random.default_rng(NO1 + 7 * NC)
+    amp = rng.uniform(0.1, 1, (nB, NC))
+    mu = rng.uniform(3000, 9000, (nB, 1)) + rng.uniform(-400, 400, (nB, NC))
+    sig = rng.uniform(50, 300, (nB, NC))
+    norms = np.sqrt(2 * np.pi) * np.sum(amp * sig, axis=1)
+    lines = rng.uniform(3000, 7000, NL)
+    args = (NC, NL, 1e3, 1e2, amp, mu, sig, lines, np.full(NL, 20.0), norms)
+    b1, b2 = rng.integers(0, nB, NO1), rng.integers(0, nB, NO2)
+    fz1, fz2 = 1 + rng.uniform(0, 3, NO1), 1 + rng.uniform(0, 3, NO2)
+    want = [rng.uniform(0, 1e-3, (NO1, NO2)) for _ in range(5)]
+    got = [w.copy() for w in want]
+    orc.kernelparts(NO1, NO2, *args, b1, fz1, b2, fz2, True, *want)
+    kernelparts(NO1, NO2, *args, b1, fz1, b2, fz2, True, *got)
+    for k, (g_, w_) in enumerate(zip(got, want)):
+        # D_alpha_z (k == 4, unused by the pipeline) is a signed sum with cancellation: its
+        # entries near zero carry the rounding noise of the large terms
+        atol = 1e-12 * np.abs(w_).max() if k == 4 else 1e-300
+        np.testing.assert_allclose(g_, w_, rtol=RTOL, atol=atol)
+    wd = [np.zeros(NO1) for _ in range(4)]
+    gd = [np.zeros(NO1) for _ in range(4)]
+    orc.kernelparts_diag(NO1, *args, b1, fz1, True, *wd)
+    kernelparts_diag(NO1, *args, b1, fz1, True, *gd)
+    for g_, w_ in zip(gd, wd):
+        np.testing.assert_allclose(g_, w_, rtol=RTOL, atol=1e-300)
+
+
+@pytest.mark.parametrize("nz,nt,nf", [(1, 1, 1), (3, 1000, 2), (751, 40, 5), (60, 17, 28)])
+def test_like_dropin_random_shapes(orc, nz, nt, nf):
+    """Any nf (the G10-style 28 bands included), pipeline-like dynamic range."""
+    from delight_b200.utils_cy import approx_flux_likelihood_cy
+    rng = np.random.default_rng(nz * 31 + nf)
+    f_obs = rng.uniform(1, 2, nf) * 4e-5
+    f_var = (0.05 * f_obs) ** 2
+    f_mod = rng.uniform(0.5, 2, (nz, nt, nf)) * 1e5 * rng.uniform(.3, 3, (nz, nt, 1))
+    f_cov = (f_mod * rng.uniform(1e-4, 1e-2, (nz, nt, nf))) ** 2
+    eh, ev = rng.uniform(.5, 2, nz), rng.uniform(.1, .5, nz)
+    want = np.zeros((nz, nt))
+    got = np.zeros((nz, nt))
+    orc.approx_flux_likelihood_cy(want, nz, nt, nf, f_obs, f_var, f_mod, f_cov, eh, ev)
+    approx_flux_likelihood_cy(got, nz, nt, nf, f_obs, f_var, f_mod, f_cov, ell_hat=eh, ell_var=ev)
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-300)
+
+
+def test_dropin_empty_inputs_are_noops():
+    from delight_b200.utils_cy import approx_flux_likelihood_cy, find_positions
+    from delight_b200.photoz_kernels_cy import kernelparts
+    like = np.full((0, 4), 7.0)
+    approx_flux_likelihood_cy(like, 0, 4, 2, np.ones(2), np.ones(2), np.ones((0, 4, 2)),
+                              np.ones((0, 4, 2)), np.ones(0), np.ones(0))
+    p = np.full(3, 9, dtype=np.int64)
+    find_positions(0, 5, np.ones(3), p, np.arange(5.0))
+    assert np.all(p == 9)
+    outs = [np.full((0, 3), 1.0) for _ in range(5)]
+    kernelparts(0, 3, 2, 1, 1e3, 1e2, np.ones((1, 2)), np.ones((1, 2)), np.ones((1, 2)),
+                np.ones(1), np.ones(1), np.ones(1), np.zeros(0, dtype=np.int64), np.ones(0),
+                np.zeros(3, dtype=np.int64), np.ones(3), True, *outs)
