@@ -58,13 +58,18 @@ constexpr int ZJ_SMALL = DL_ZJ;   // redshifts a lane processes jointly (indepen
 constexpr int ZJ_LARGE = 1;       //   NF <= 8 / NF > 8 (register budget: 8 NF ZJ registers of model values)
 constexpr int FZC = 32 * FZT;     // redshifts per CTA chunk
 constexpr int FSTAGES = DL_STAGES;  // TMA ring depth
-constexpr int FPREF = FSTAGES - 2;  // prefetch distance in steps
+#ifndef DL_PREF
+#define DL_PREF (DL_STAGES - 2)
+#endif
+constexpr int FPREF = DL_PREF;      // prefetch distance in steps (< FSTAGES)
 // Warp 0 also issues the TMA copies of every stage (6.5 % of its time, measured with
 // -DDL_DBGWAIT), which makes it the straggler the other seven warps wait for (~8 % of their
 // time; they free issue slots while they wait, so the net loss is ~3 %).  DL_ASYM=1 gives the
 // warp DL_LIGHTWARP one target less; measured round 1: lightening warp 0 or warp 4 (same
-// scheduler as warp 0) makes the kernel 1.8-2x SLOWER (warp 0 is then starved: the others wait
-// 60 % of the time for it, results identical), lightening warp 7 costs 9 %.  Default: off.
+// scheduler as warp 0) makes the kernel 1.8-2x SLOWER (warp 0 then needs twice the cycles per
+// cell and the others wait 60 % of the time for it; results identical; independent of the
+// prefetch distance and of try_wait vs test_wait polling -- cause not understood), lightening
+// warp 7 costs 9 %.  Default: off.
 #ifndef DL_ASYM
 #define DL_ASYM 0
 #endif
