@@ -706,3 +706,45 @@ def test_dropin_empty_inputs_are_noops():
     kernelparts(0, 3, 2, 1, 1e3, 1e2, np.ones((1, 2)), np.ones((1, 2)), np.ones((1, 2)),
                 np.ones(1), np.ones(1), np.ones(1), np.zeros(0, dtype=np.int64), np.ones(0),
                 np.zeros(3, dtype=np.int64), np.ones(3), True, *outs)
+
+
+@pytest.mark.parametrize("scale_obs,scale_mod,snr,nf", [
+    (1e-17, 1e-17, 20.0, 8),       # cgs-like flux units: variances ~1e-37, products over 8 bands
+    (1e+12, 1e+3, 5.0, 6),         # huge fluxes, ell ~ 1e9
+    (4e-5, 1e5, 2000.0, 6),        # S/N 2000: chi2 differences ~1e7, almost everything underflows
+    (4e-5, 1e5, 0.5, 5),           # S/N 0.5: flat likelihood
+])
+def test_fused_extreme_dynamic_range(orc, scale_obs, scale_mod, snr, nf):
+    """Unit systems and signal-to-noise regimes far from the mocks: the per-target power-of-two
+    rescaling must keep every intermediate in range."""
+    from delight_b200 import apply
+    rng = np.random.default_rng(int(snr * 10) + nf)
+    nO, nT, nz, nB = 12, 40, 130, nf
+    zgrid = np.linspace(0.01, 2.0, nz)
+    shape = rng.uniform(0.5, 2.0, (1, nT, nB)) * (1 + 0.5 * np.sin(
+        zgrid[:, None, None] * rng.uniform(1, 4, (1, nT, nB))))
+    mm = shape * scale_mod
+    mc = (mm * rng.uniform(1e-3, 3e-2, (nz, nT, nB))) ** 2
+    zt = rng.uniform(0.01, 2.0, nT)
+    src, zi = rng.integers(0, nT, nO), rng.integers(0, nz, nO)
+    true = mm[zi, src] * (scale_obs / scale_mod)
+    fv = (true / snr) ** 2
+    fl = np.abs(true * (1 + rng.standard_normal(true.shape) / snr)) + 1e-3 * true
+    bands = np.tile(np.arange(nB), (nO, 1))
+    nfs = np.full(nO, nB)
+    K = 10
+    ref = orc.apply_fused(fl, fv, nfs, bands, mm, mc, orc.z_prior(zgrid, zt, 0.5), zgrid,
+                          np.ones(nz), np.full(nz, 0.25), K, want_evid=True)
+    assert np.isfinite(ref["pdf"]).all() and ref["pdf"].max() > 0
+    grid = apply.ModelGrid.from_legacy(mm, mc)
+    res = apply.apply_fused(grid, grid.gaussian_prior(zgrid, zt, 0.5), zgrid,
+                            apply.Targets(fl, fv, bands, nfs), ell_var=0.25, K=K, want_evid=True)
+    assert np.isfinite(res["pdf"]).all()
+    # chi2 is a difference of O(nf * snr^2) terms: the absolute rounding error of the exponent
+    # grows with snr^2 in the reference too
+    rtol = max(RTOL, 1e-13 * nf * snr ** 2)
+    scale = ref["pdf"].max(axis=1, keepdims=True)
+    assert np.all(np.abs(res["pdf"] - ref["pdf"]) <= rtol * ref["pdf"] + 1e-290 * scale)
+    solid = ref["top_ev"] > 1e-250 * ref["top_ev"][:, :1]
+    if snr < 1000:
+        np.testing.assert_array_equal(res["top_idx"][solid], ref["top_idx"][solid])
