@@ -203,11 +203,12 @@ class FusedWorkspace:
 
 def apply_fused(grid, prior, zgrid, targets, ell_hat=1.0, ell_var=1.0, K=0, want_evid=False,
                 want_metrics=False, workspace=None, nsplit=None, out_device=False,
-                confidence_levels=None):
+                confidence_levels=None, cov_scale=1.0):
     """Likelihood + PDF + evidences + top-K for all `targets` against the whole model grid.
 
     ell_hat / ell_var: scalars (what delight-apply.py:119-144 passes: 1 and ellPriorSigma^2) or
     arrays [nz] (the general operator signature, utils_cy.pyx:92-93).
+    cov_scale: factor on the model variance (delight-optimize.py:122 passes V_C * model_covar).
     confidence_levels (with want_metrics): the cfg's confidenceLevels; the metrics then carry the
     reference's 7 + nCL columns of computeMetrics (utils.py:213-227) followed by the argmax index.
     Returns dict(pdf [nO, nz], top_idx [nO, K] int64, top_ev [nO, K], evid [nO, nT] | None,
@@ -284,7 +285,7 @@ def apply_fused(grid, prior, zgrid, targets, ell_hat=1.0, ell_var=1.0, K=0, want
             _lib.check(L.dl_like_fused_dev(
                 n, nT, nz, nB, nf, bands_c, _lib.ptr(obs[t0:t0 + n]), _lib.ptr(var[t0:t0 + n]),
                 _lib.ptr(grid.grid), _lib.ptr(prior), _lib.ptr(zg), ehs, evs, _lib.ptr(eh),
-                _lib.ptr(ev), ns, K, _lib.ptr(g_pdf[t0:t0 + n]), nz,
+                _lib.ptr(ev), float(cov_scale), ns, K, _lib.ptr(g_pdf[t0:t0 + n]), nz,
                 _lib.ptr(g_evid[t0:t0 + n]) if g_evid is not None else None,
                 _lib.ptr(g_idx[t0:t0 + n]) if K > 0 else None,
                 _lib.ptr(g_ev[t0:t0 + n]) if K > 0 else None,

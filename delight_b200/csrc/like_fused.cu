@@ -410,7 +410,8 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
 // out: tconst [nO][tc_stride(NF)], layout documented at tc_stride()
 __global__ void prep_targets_kernel(int nO, int NF, const double* __restrict__ obs,
                                     const double* __restrict__ var, double ell_hat,
-                                    double ell_var, double* __restrict__ tconst) {
+                                    double ell_var, double cov_scale,
+                                    double* __restrict__ tconst) {
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
     if (o >= nO) return;
     const int TCS = tc_stride(NF);
@@ -432,7 +433,7 @@ __global__ void prep_targets_kernel(int nO, int NF, const double* __restrict__ o
         tc[2 * NF + 4 * f + 3] = 0.0;
     }
     tc[6 * NF + 0] = -0.5 * ic;
-    tc[6 * NF + 1] = ic;
+    tc[6 * NF + 1] = ic * cov_scale;   // ell^2 * (cov_scale * model variance) / c
     tc[6 * NF + 2] = c * (ell_hat / ell_var);
     tc[6 * NF + 3] = c / ell_var;
     tc[6 * NF + 4] = c * (ell_hat * ell_hat / ell_var);
@@ -950,13 +951,15 @@ int dl_zprior_dev(long long nT, long long nz, const double* zgrid, const double*
 //   grid         [nT][2nB][nzp] device, prior [nT][nzp] device (nzp = dl_fused_padded_nz(nz))
 //   zgrid        [nz] device
 //   ell_hat/ell_var: scalars, or (ell_hat_z, ell_var_z != NULL) device vectors [nz]
+//   cov_scale    factor on the model variance (1 in delight-apply; V_C in delight-optimize.py:122)
 //   outputs (device): pdf [nO][ld_pdf]; evid [nO][nT] or NULL; top_idx [nO][K] int64,
 //                     top_ev [nO][K] (K may be 0)
 int dl_like_fused_dev(long long nO, long long nT, long long nz, long long nB, int nf,
                       const int* bands, const double* obs, const double* var,
                       const double* grid, const double* prior, const double* zgrid,
                       double ell_hat, double ell_var, const double* ell_hat_z,
-                      const double* ell_var_z, int nsplit, int K, double* pdf, long long ld_pdf,
+                      const double* ell_var_z, double cov_scale, int nsplit, int K, double* pdf,
+                      long long ld_pdf,
                       double* evid, long long* top_idx, double* top_ev, void* workspace,
                       long long workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -965,6 +968,7 @@ int dl_like_fused_dev(long long nO, long long nT, long long nz, long long nB, in
     DL_REQUIRE(nsplit >= 1 && nsplit <= nT, "bad nsplit");
     DL_REQUIRE(K >= 0 && K <= TK_MAXK && K <= nT, "0 <= K <= min(nT, 1024)");
     DL_REQUIRE(ld_pdf >= nz, "ld_pdf < nz");
+    DL_REQUIRE(cov_scale >= 0.0, "cov_scale < 0");
     const bool zdep = ell_hat_z != nullptr && ell_var_z != nullptr;
     const long long need = dl_fused_workspace_bytes(nO, nT, nz, nsplit, evid != nullptr || K == 0);
     DL_REQUIRE(workspace && workspace_bytes >= need, "workspace too small");
@@ -991,7 +995,7 @@ int dl_like_fused_dev(long long nO, long long nT, long long nz, long long nB, in
     dl_count_launch();
 
     prep_targets_kernel<<<(unsigned)((nO + 127) / 128), 128, 0, stream>>>(
-        (int)nO, nf, obs, var, zdep ? 1.0 : ell_hat, zdep ? 1.0 : ell_var, tconst);
+        (int)nO, nf, obs, var, zdep ? 1.0 : ell_hat, zdep ? 1.0 : ell_var, cov_scale, tconst);
     DL_CUDA_CHECK(cudaGetLastError());
     dl_count_launch();
 

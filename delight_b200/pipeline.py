@@ -14,7 +14,9 @@ semantics of delight/io.py for the keys and columns this path uses:
     fewer than two valid bands are skipped; variance += (training_extraFracFluxError * flux)^2
     for targets too (the reference uses the training key for both prefixes, io.py:350-351);
   * gpparams rows: `%i` + `%.12e` columns (delight-learn.py:48,130);
-  * outputs: `%.2e` PDFs / metrics / evidences, `%i` indices (delight-apply.py:222-233).
+  * outputs: `%.2e` PDFs / metrics / evidences, `%i` indices (delight-apply.py:222-233);
+  * any catalogue / gpparams / output path ending in `.npy` is read / written as a binary NumPy
+    array with the same rows and columns (text parsing dominates at 10^6 objects).
 Rows of skipped objects stay zero at the END of the output arrays, as in the reference (its
 `loc` counter only advances on yielded objects).
 """
@@ -110,7 +112,7 @@ def read_catalogue(p, prefix, first=0, last=None):
     """Catalogue rows [first, last) -> packed apply.Targets (io.py:305-351 semantics).
     Returns (targets, n_lines) where n_lines counts file rows in the range."""
     band_idx, cols, vcols, zcol, refcol = column_positions(p, prefix)
-    data = np.loadtxt(p[prefix + "catFile"], ndmin=2)[first:last]
+    data = _load(p[prefix + "catFile"])[first:last]
     n_lines = data.shape[0]
     flux, var = data[:, cols], data[:, vcols]
     mask = np.isfinite(flux) & np.isfinite(var) & (flux > 0.0) & (var > 0.0)
@@ -149,7 +151,7 @@ def learn(cfg_path, write=True):
     p = parse_params(cfg_path)
     rank, size = _dist.init()
     gpm, _ = make_gp(p)
-    n_total = sum(1 for _ in open(p["training_catFile"]))
+    n_total = _count_rows(p["training_catFile"])
     first, last = _dist.partition(n_total, rank, size)            # delight-learn.py:31-33
     cat, n_lines = read_catalogue(p, "training_", first, last)
     import torch
@@ -161,7 +163,7 @@ def learn(cfg_path, write=True):
         rows = rows.cpu().numpy()
         if write:
             fmt = "%i " + "%.12e " * (rows.shape[1] - 1)          # delight-learn.py:48
-            np.savetxt(p["training_paramFile"], rows, fmt=fmt)
+            _save(p["training_paramFile"], rows, fmt)
     return rows if rank == 0 else None
 
 
@@ -180,10 +182,10 @@ def apply(cfg_path, write=True, cap_training_like_reference=True):
     rank, size = _dist.init()
     import torch
     gpm, zgrid = make_gp(p)
-    n_train = sum(1 for _ in open(p["training_paramFile"]))
-    n_target = sum(1 for _ in open(p["target_catFile"]))
+    n_train = _count_rows(p["training_paramFile"])
+    n_target = _count_rows(p["target_catFile"])
     tr_last = int(min(n_train, n_target)) if cap_training_like_reference else n_train
-    rows = np.loadtxt(p["training_paramFile"], ndmin=2)[:tr_last]
+    rows = _load(p["training_paramFile"])[:tr_last]
     rows = rows[rows[:, 0] >= 1]                                   # unused (skipped) rows
     ncol = gpm.numCol
     if rows.shape[1] < ncol:
@@ -216,13 +218,74 @@ def apply(cfg_path, write=True, cap_training_like_reference=True):
     out = dict(pdfs=pdfs.cpu().numpy(), top_idx=idx.cpu().numpy(), top_ev=ev.cpu().numpy(),
                metrics=met.cpu().numpy() if with_z else None)
     if write:                                                      # delight-apply.py:222-233
-        np.savetxt(p["redshiftpdfFile"], out["pdfs"], fmt="%.2e")
+        _save(p["redshiftpdfFile"], out["pdfs"], "%.2e")
         if with_z:
-            np.savetxt(p["metricsFile"], out["metrics"], fmt="%.2e")
+            _save(p["metricsFile"], out["metrics"], "%.2e")
         if p["useCompression"] and not p["compressionFilesFound"]:
-            np.savetxt(p["compressMargLikFile"], out["top_ev"], fmt="%.2e")
-            np.savetxt(p["compressIndicesFile"], out["top_idx"], fmt="%i")
+            _save(p["compressMargLikFile"], out["top_ev"], "%.2e")
+            _save(p["compressIndicesFile"], out["top_idx"], "%i")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# hyper-parameter sweep  (scripts/delight-optimize.py:52-128)
+# ------------------------------------------------------------------------------------------------
+def sweep(cfg_path, ellPriorSigmas=(1.0, 10.0), V_Cs=(0.1, 1.0), zPriorSigmas=(0.1, 1.0)):
+    """The likelihood part of delight-optimize.py as a multi-configuration run on one resident
+    model grid: for every (ellPriorSigma, V_C, zPriorSigma) one fused pass over all targets with
+    `V_C * model_covar` (:122), prior width zPriorSigma (:124-126) and the full computeMetrics
+    row per target (:131-134).  As in the reference, V_C only rescales the model variance (the
+    script sets `gp.var_C`, which the kernel object never reads) and the extraFracFluxError loop
+    has no effect on the catalogue reader, so the grid is fitted and predicted once.
+    Returns {(ellPriorSigma, V_C, zPriorSigma): metrics [n_valid_targets, 7 + nCL]} on rank 0
+    (targets sharded over ranks)."""
+    p = parse_params(cfg_path)
+    rank, size = _dist.init()
+    gpm, zgrid = make_gp(p)
+    n_train = _count_rows(p["training_catFile"])
+    cat, _ = read_catalogue(p, "training_", 0, n_train)
+    grid, train_z = gpm.predict(gpm.fit(cat, out_device=True))
+    n_target = _count_rows(p["target_catFile"])
+    first, last = _dist.partition(n_target, rank, size)
+    targets, n_lines = read_catalogue(p, "target_", first, last)
+    targets.to_device()
+    ws = _apply.FusedWorkspace()
+    import torch
+    out = {}
+    for zs in zPriorSigmas:
+        prior = grid.gaussian_prior(zgrid, train_z, zs)
+        for es in ellPriorSigmas:
+            for vc in V_Cs:
+                res = _apply.apply_fused(grid, prior, zgrid, targets, ell_hat=1.0,
+                                         ell_var=es ** 2, K=0, want_metrics=True,
+                                         confidence_levels=p["confidenceLevels"], cov_scale=vc,
+                                         workspace=ws, out_device=True)
+                m = res["metrics"][:, :7 + len(p["confidenceLevels"])]
+                pad = torch.zeros((n_lines, m.shape[1]), dtype=torch.float64, device="cuda")
+                pad[:m.shape[0]] = m
+                g = _dist.gather_rows(pad, n_target)
+                if rank == 0:
+                    g = g.cpu().numpy()
+                    out[(es, vc, zs)] = g[g[:, 3] != 0] if size > 1 else g[:m.shape[0]]
+    return out if rank == 0 else None
+
+
+def _save(path, arr, fmt):
+    """Text in the reference's format, or binary when the cfg names a .npy file."""
+    if path.endswith(".npy"):
+        np.save(path, arr)
+    else:
+        np.savetxt(path, arr, fmt=fmt)
+
+
+def _count_rows(path):
+    if path.endswith(".npy"):
+        return int(np.load(path, mmap_mode="r").shape[0])
+    return sum(1 for _ in open(path))
+
+
+def _load(path):
+    return np.load(path) if path.endswith(".npy") else np.loadtxt(path, ndmin=2)
 
 
 def main(argv=None):

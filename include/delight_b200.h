@@ -140,12 +140,15 @@ int dl_zprior_dev(long long nT, long long nz, const double* zgrid, const double*
  * targets that share the band list `bands` (HOST array, nf <= 16 entries).
  *   obs/var [nO][nf]; ell_hat/ell_var scalars, or device vectors ell_hat_z/ell_var_z [nz]
  *   pdf [nO][ld_pdf] out; evid [nO][nT] out or NULL; top_idx [nO][K] / top_ev [nO][K] out
- *   (K = 0: skipped).  Ties: descending evidence, equal -> larger index first. */
+ *   (K = 0: skipped).  Ties: descending evidence, equal -> larger index first.
+ *   cov_scale multiplies the model variance (1.0 for delight-apply; delight-optimize.py:122
+ *   passes V_C * model_covar). */
 int dl_like_fused_dev(long long nO, long long nT, long long nz, long long nB, int nf,
                       const int* bands, const double* obs, const double* var,
                       const double* grid, const double* prior, const double* zgrid,
                       double ell_hat, double ell_var, const double* ell_hat_z,
-                      const double* ell_var_z, int nsplit, int K, double* pdf, long long ld_pdf,
+                      const double* ell_var_z, double cov_scale, int nsplit, int K, double* pdf,
+                      long long ld_pdf,
                       double* evid, long long* top_idx, double* top_ev, void* workspace,
                       long long workspace_bytes, void* stream);
 

@@ -748,3 +748,44 @@ def test_fused_extreme_dynamic_range(orc, scale_obs, scale_mod, snr, nf):
     solid = ref["top_ev"] > 1e-250 * ref["top_ev"][:, :1]
     if snr < 1000:
         np.testing.assert_array_equal(res["top_idx"][solid], ref["top_idx"][solid])
+
+
+def test_cov_scale_and_sweep(orc, sdss, tmp_path):
+    """cov_scale (= V_C * model_covar of delight-optimize.py:122) vs the oracle, the
+    multi-configuration sweep driver, and binary (.npy) catalogue / output files."""
+    from oracle import pipeline as refpipe
+    from delight_b200 import apply, pipeline
+    g = sdss
+    nz = g["zgrid"].size
+    grid = apply.ModelGrid.from_legacy(g["model_mean"], g["model_covar"])
+    prior = grid.gaussian_prior(g["zgrid"], g["gp_rows"][:, 1], 0.1)
+    t = apply.Targets(g["ta_flux"], g["ta_var"], g["ta_bands"], g["ta_nb"], g["ta_z"])
+    res = apply.apply_fused(grid, prior, g["zgrid"], t, ell_var=100.0, cov_scale=0.1, K=0)
+    ref = orc.apply_fused(g["ta_flux"], g["ta_var"], g["ta_nb"], g["ta_bands"], g["model_mean"],
+                          0.1 * g["model_covar"], orc.z_prior(g["zgrid"], g["gp_rows"][:, 1], 0.1),
+                          g["zgrid"], np.ones(nz), np.full(nz, 100.0), 0)
+    assert_close(res["pdf"], ref["pdf"], ref["pdf"].max(axis=1, keepdims=True) * 1e-290)
+    # sweep driver on files, with the target catalogue and the PDFs in binary form
+    wd = str(tmp_path)
+    cfg = refpipe.make_workdir(wd, bands=refpipe.SDSS,
+                               train_bands=["U_SDSS", "G_SDSS", "I_SDSS"], refband="I_SDSS",
+                               numObjects=24, dz=0.01, nzGP=40, Ncompress=int(g["Ncompress"]),
+                               copy_data=False)
+    refpipe.write_preprocessed(wd, refpipe.SDSS, g["amp"], g["mu"], g["sig"], g["tmpl"])
+    np.savetxt(wd + "/galaxies-fluxredshifts.txt", g["train_cat"])
+    np.save(wd + "/targets.npy", g["target_cat"])
+    txt = open(cfg).read().replace(wd + "/galaxies-fluxredshifts2.txt", wd + "/targets.npy") \
+                          .replace(wd + "/redshiftpdfs.txt", wd + "/redshiftpdfs.npy")
+    open(cfg, "w").write(txt)
+    pipeline.learn(cfg)
+    out = pipeline.apply(cfg)
+    n = g["pdfs"].shape[0]
+    np.testing.assert_allclose(np.load(wd + "/redshiftpdfs.npy")[:n], g["pdfs"], rtol=1e-6,
+                               atol=1e-290 * g["pdfs"].max())
+    sw = pipeline.sweep(cfg, ellPriorSigmas=(float(g["ellPriorSigma"]),), V_Cs=(1.0, 0.1),
+                        zPriorSigmas=(float(g["zPriorSigma"]), 0.1))
+    assert len(sw) == 4
+    key = (float(g["ellPriorSigma"]), 1.0, float(g["zPriorSigma"]))
+    np.testing.assert_allclose(sw[key], out["metrics"][:n], rtol=1e-9)
+    other = sw[(float(g["ellPriorSigma"]), 0.1, 0.1)]
+    assert other.shape == sw[key].shape and not np.allclose(other[:, 1], sw[key][:, 1])
