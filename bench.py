@@ -221,15 +221,37 @@ def cpu_baseline_sample(data, model_mean, model_covar, zt, budget_s=20.0):
     cat = workloads.mock_catalogue(64, data, seed=2)
     set_omp_threads(os.cpu_count() or 1)
     reference_step(cy_like, model_mean, model_covar, prior, zgrid, cat, 0, 1)     # warm
-    n, t0 = 0, time.perf_counter()
+    n, t0, outs = 0, time.perf_counter(), []
     while n < 64 and (time.perf_counter() - t0 < budget_s or n < 3):
-        reference_step(cy_like, model_mean, model_covar, prior, zgrid, cat, n, 1)
+        outs += reference_step(cy_like, model_mean, model_covar, prior, zgrid, cat, n, 1)
         n += 1
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "galaxies/s", "cores": os.cpu_count() or 1, "kind": kind,
+    base = {"value": n / dt, "unit": "galaxies/s", "cores": os.cpu_count() or 1, "kind": kind,
             "sample": "%d targets against the full %d x %d x %d grid (loop body of "
                       "delight-apply.py:114-162 incl. its per-target fancy-index grid copies), "
                       "%.1f s" % (n, nz, nT, nB, dt)}
+    return base, cat, outs
+
+
+def parity_check(gpu, outs):
+    """The GPU path vs what the CPU reference just produced for the same targets at the full
+    bench shape: PDFs (relative, above 1e-290 x max) and top-K indices where the evidence is
+    representable (the reference's argsort is unstable on exact ties)."""
+    pdf_ref = np.stack([o[0] for o in outs])
+    idx_ref = np.stack([o[1] for o in outs])
+    ev_ref = np.stack([o[2] for o in outs])
+    n = pdf_ref.shape[0]
+    pdf = gpu["pdf"][:n]
+    scale = pdf_ref.max(axis=1, keepdims=True)
+    big = pdf_ref > 1e-290 * scale
+    rel = np.abs(pdf - pdf_ref)[big] / pdf_ref[big]
+    solid = ev_ref > 1e-250 * ev_ref[:, :1]
+    return {"targets": int(n), "pdf_max_rel_err": float(rel.max()),
+            "evid_max_rel_err": float((np.abs(gpu["top_ev"][:n] - ev_ref)[solid]
+                                       / ev_ref[solid]).max()),
+            "topk_indices_equal": bool(np.array_equal(gpu["top_idx"][:n][solid],
+                                                      idx_ref[solid])),
+            "tolerance": 1e-9}
 
 
 def other_configs(data):
@@ -448,13 +470,18 @@ def run_b200(args):
                                                                   + N_COMPRESS * 16 + 64),
             "hbm_peak_GBs": peaks.get("hbm_gbs"),
         }
-        cpu = None
+        cpu, parity = None, None
         if world == 1 and not args.no_cpu_baseline:
             G = grid.grid[:, :, :nz].cpu().numpy()                 # [nT, 2nB, nz]
             mm = np.ascontiguousarray(G[:, :nB, :].transpose(2, 0, 1))
             mc = np.ascontiguousarray(G[:, nB:, :].transpose(2, 0, 1))
             del G
-            cpu = cpu_baseline_sample(data, mm, mc, train_z.cpu().numpy())
+            cpu, pcat, pouts = cpu_baseline_sample(data, mm, mc, train_z.cpu().numpy())
+            n = len(pouts)
+            g = apply.apply_fused(grid, prior, zg_dev,
+                                  apply.Targets.full(pcat["fluxes"][:n], pcat["fluxes_var"][:n]),
+                                  ell_hat=1.0, ell_var=ELL_VAR, K=N_COMPRESS, workspace=ws)
+            parity = parity_check(g, pouts)
         line = {
             "metric": "galaxy-PDFs/sec", "value": value, "unit": "galaxies/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
@@ -476,6 +503,7 @@ def run_b200(args):
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "parity_check": parity,
             "other_configs": extras,
         }
         print(json.dumps(line))
