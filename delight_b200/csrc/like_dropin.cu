@@ -92,8 +92,11 @@ int dl_approx_flux_likelihood_dev(double* like, long long nz, long long nt, long
     DL_REQUIRE(like && f_obs && f_obs_var && f_mod && f_mod_covar && ell_hat && ell_var && scratch,
                "null pointer");
     DL_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 8, stream));
+    int dev = 0, sms = 148;
+    DL_CUDA_CHECK(cudaGetDevice(&dev));
+    DL_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     long long blocks = (ncell + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;   // grid-stride, 16 CTAs/SM
     loglike_kernel<<<(unsigned)blocks, 256, 2 * nf * sizeof(double), stream>>>(
         ncell, (int)nt, (int)nf, f_obs, f_obs_var, f_mod, f_mod_covar, ell_hat, ell_var, like,
         (unsigned long long*)scratch);
