@@ -45,6 +45,14 @@ struct DevBuf {
 
 #define TRY(x) do { int _rc = (x); if (_rc != DL_OK) return _rc; } while (0)
 
+// host-side range check of index arrays (the reference runs with boundscheck=False and would
+// read out of bounds; on a GPU that is a fault, so the host entry points refuse instead)
+static bool in_range(const long long* v, long long n, long long lo, long long hi) {
+    for (long long i = 0; i < n; ++i)
+        if (v[i] < lo || v[i] >= hi) return false;
+    return true;
+}
+
 extern "C" {
 
 const char* dl_last_error(void) { return g_err; }
@@ -95,6 +103,7 @@ int dl_kernelparts_host(long long NO1, long long NO2, long long NC, long long NL
                         double* D_alpha_C, double* D_alpha_L, double* D_alpha_z) {
     DL_REQUIRE(NO1 >= 0 && NO2 >= 0 && nB >= 1, "bad sizes");
     if (NO1 * NO2 == 0) return DL_OK;
+    DL_REQUIRE(in_range(b1, NO1, 0, nB) && in_range(b2, NO2, 0, nB), "band index out of range");
     DevBuf da, dm, ds, dl_, dn, db1, df1, db2, df2, o[5];
     TRY(da.upload(amp, nB * NC * 8));
     TRY(dm.upload(mu, nB * NC * 8));
@@ -127,6 +136,7 @@ int dl_kernelparts_diag_host(long long NO1, long long NC, long long NL, double a
                              double* KC, double* D_alpha_C, double* D_alpha_L) {
     DL_REQUIRE(NO1 >= 0 && nB >= 1, "bad sizes");
     if (NO1 == 0) return DL_OK;
+    DL_REQUIRE(in_range(b1, NO1, 0, nB), "band index out of range");
     DevBuf da, dm, ds, dl_, dn, db1, df1, o[4];
     TRY(da.upload(amp, nB * NC * 8));
     TRY(dm.upload(mu, nB * NC * 8));
@@ -169,6 +179,9 @@ int dl_kernel_parts_interp_host(long long NO1, long long NO2, double* Kinterp,
                                 long long nzg) {
     DL_REQUIRE(NO1 >= 0 && NO2 >= 0 && nB >= 1 && nzg >= 2, "bad sizes");
     if (NO1 * NO2 == 0) return DL_OK;
+    DL_REQUIRE(in_range(b1, NO1, 0, nB) && in_range(b2, NO2, 0, nB), "band index out of range");
+    DL_REQUIRE(in_range(p1s, NO1, 0, nzg - 1) && in_range(p2s, NO2, 0, nzg - 1),
+               "bin position out of range");
     DevBuf dk, db1, df1, dp1, db2, df2, dp2, dg, dG;
     TRY(dk.alloc((size_t)NO1 * NO2 * 8));
     TRY(db1.upload(b1, NO1 * 8));

@@ -125,6 +125,9 @@ __global__ void __launch_bounds__(FIT_WARPS * 32) gp_fit_kernel(
         const double oe = __shfl_xor_sync(0xffffffffu, bestell, s);
         if (ov < bestv || (ov == bestv && ot < bestt)) { bestv = ov; bestt = ot; bestell = oe; }
     }
+    // all scores NaN (e.g. non-positive variances): np.argmin would return 0; keep indices in
+    // range and let the NaN propagate into the row (the host reports it)
+    if (bestt >= nt) { bestt = 0; bestell = nan(""); }
     const double ell = bestell;
     // A = K(X) + diag(Yvar)   (photoz_gp.py:205-206, photoz_kernels.py:221-231, 338-340)
     const double fz = 1.0 + z;

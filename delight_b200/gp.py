@@ -77,6 +77,13 @@ class PhotozGPBatched:
                 _lib.ptr(self.d_zgp), _lib.ptr(self.d_fz), _lib.ptr(self.d_tmpl),
                 _lib.ptr(self.d_zgrid), self.V_C, self.V_L, *[_lib.ptr(a) for a in args],
                 _lib.ptr(rows), self.numCol, _lib.stream_ptr()))
+        bad = ~torch.isfinite(rows).all(dim=1)
+        if bool(bad.any().item()):
+            # scipy.linalg.cholesky raises LinAlgError in the reference (photoz_gp.py:209)
+            idx = torch.nonzero(bad).flatten()[:8].cpu().tolist()
+            raise _lib.DelightB200Error(
+                "GP fit failed (K + diag(Yvar) not positive definite or non-finite input) for "
+                "%d training galaxies, first rows: %s" % (int(bad.sum().item()), idx))
         return rows if out_device else rows.cpu().numpy()
 
     def predict(self, rows):
@@ -86,6 +93,17 @@ class PhotozGPBatched:
             rows = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.float64))
         rows = rows.cuda().contiguous()
         nT, numCol = rows.shape
+        if nT:
+            # range-check what the kernel will use as indices (a corrupt gpparams file must not
+            # become an out-of-bounds read on the device)
+            B = rows[:, 0]
+            col = torch.arange(self.nB, device="cuda")[None, :]
+            bands = rows[:, 3:3 + self.nB]
+            used = col < B[:, None]
+            if bool(((B < 0) | (B > self.nB) | (B != B.round())).any().item()) or \
+                    bool((used & ((bands < 0) | (bands >= self.nB) | (bands != bands.round())))
+                         .any().item()):
+                raise ValueError("gpparams rows: band count / band indices out of range")
         nzp = int(_lib.lib().dl_fused_padded_nz(self.nz))
         grid = torch.empty((nT, 2 * self.nB, nzp), dtype=torch.float64, device="cuda")
         train_z = torch.empty(nT, dtype=torch.float64, device="cuda")

@@ -425,6 +425,19 @@ def test_gp_fit_matches_reference_learn(sdss, gp_sdss):
         np.testing.assert_allclose(core, want, rtol=RTOL, atol=1e-12 * np.abs(want).max())
 
 
+def test_gp_fit_reports_failed_cholesky(sdss, gp_sdss):
+    """A non-positive-definite K + diag(Yvar) raises (the reference's scipy call raises
+    LinAlgError) instead of writing NaN rows."""
+    from delight_b200 import gp, _lib
+    g = sdss
+    var = g["tr_var"].copy()
+    var[2, :int(g["tr_nb"][2])] = -1e30          # bypasses Targets' own validation below
+    cat = gp.catalogue(g["tr_flux"], np.abs(var), g["tr_bands"], g["tr_nb"], g["tr_z"])
+    cat.fluxes_var = var
+    with pytest.raises(_lib.DelightB200Error, match="GP fit failed"):
+        gp_sdss.fit(cat)
+
+
 def test_gp_predict_matches_reference_model_grid(sdss, gp_sdss):
     """dl_gp_predict_dev (setCore + predictAndInterpolate) vs the reference's model_mean /
     model_covar, through the fused layout."""
