@@ -62,16 +62,33 @@ constexpr int FSTAGES = DL_STAGES;  // TMA ring depth
 #define DL_PREF (DL_STAGES - 2)
 #endif
 constexpr int FPREF = DL_PREF;      // prefetch distance in steps (< FSTAGES)
-// Warp 0 also issues the TMA copies of every stage (6.5 % of its time, measured with
-// -DDL_DBGWAIT), which makes it the straggler the other seven warps wait for (~8 % of their
-// time; they free issue slots while they wait, so the net loss is ~3 %).  DL_ASYM=1 gives the
-// warp DL_LIGHTWARP one target less; measured round 1: lightening warp 0 or warp 4 (same
-// scheduler as warp 0) makes the kernel 1.8-2x SLOWER (warp 0 then needs twice the cycles per
-// cell and the others wait 60 % of the time for it; results identical; independent of the
-// prefetch distance and of try_wait vs test_wait polling -- cause not understood), lightening
-// warp 7 costs 9 %.  Default: off.
+// Warp 0 also issues the TMA copies of every stage, which makes it the straggler the other
+// seven warps wait for.  Tuning switches around that (all measured at config 3):
+//   DL_ELECT=1    (default) the copies are issued by the elect.sync leader of warp 0: the compiler
+//                 then keeps the addresses in uniform registers and emits the UBLKCPs back to back
+//                 instead of a 16-instruction "for each active thread" loop per copy
+//                 (1.384 -> 1.346 s).
+//   DL_DISTPROD=1 every warp issues its share (rows warp, warp+FW, ...) of each stage and arrives
+//                 on `full` with its own expect_tx, so no warp is special (1.350 s with DL_ELECT).
+//   DL_ASYM=1     warp DL_LIGHTWARP gets one target less (1.384 s without DL_ELECT: the 3 % more
+//                 CTAs eat the gain).
+// Round-1 note: before the barrier polls were made whole-warp (see issue_stage) every one of
+// these variants measured 1.8-2.8x SLOWER, because the polling lane left its warp split in two
+// fragments for the whole compute phase.
 #ifndef DL_ASYM
 #define DL_ASYM 0
+#endif
+#ifndef DL_ROLL_O
+#define DL_ROLL_O 0
+#endif
+#ifndef DL_DISTPROD
+#define DL_DISTPROD 0
+#endif
+#ifndef DL_PRODWARP
+#define DL_PRODWARP 0
+#endif
+#ifndef DL_ELECT
+#define DL_ELECT 1
 #endif
 constexpr int FTPC = FW * FTO - DL_ASYM;    // targets per CTA
 constexpr int FTHREADS = FW * 32;
@@ -126,7 +143,7 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < FSTAGES; ++s) {
-            mbar_init(&full[s], 1);
+            mbar_init(&full[s], DL_DISTPROD ? FW : 1);
             mbar_init(&empty[s], FW);
         }
         mbar_fence_init();
@@ -148,16 +165,12 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
     __syncthreads();
 
     // ---------------------------------------------------------------------- TMA producer
-    // No dedicated producer warp (it would cost 32 registers/thread of occupancy): lane 0 of
-    // warp 0 refills, before it computes step `it`, the stage every warp released FPREF steps
-    // ago.  (Measured alternatives, round 1: "first warp to arrive claims the refill"
-    // and "the producer role rotates over the warps" are both 2.8x slower; deeper rings 3-6 %
-    // slower; a 2-D tensor-map copy of all 2 NF rows (UTMALDG) instead of 2 NF bulk copies cuts
-    // the producer's issue time from 8 % to 2 % of warp 0 and the other warps' wait on it from
-    // 9 % to 3 %, but the resulting kernel was 14 % slower at full size -- not adopted.)
+    // No dedicated producer warp (it would cost 32 registers/thread of occupancy): warp 0
+    // refills, before it computes step `it`, the stage every warp released FPREF steps ago.
+    // (Measured alternatives: deeper rings 3-6 % slower; prefetch distance 1 or 3 no change.)
     const int nsteps = t_end - t_begin;
 #ifdef DL_DBGWAIT
-    long long dbg_empty = 0, dbg_issue = 0, dbg_wait = 0;
+    long long dbg_empty = 0, dbg_issue = 0, dbg_wait = 0, dbg_div = 0;
     const long long dbg_t0 = clock64();
 #endif
     auto issue_stage = [&](int step) {
@@ -167,11 +180,35 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
 #ifdef DL_DBGWAIT
         const long long ta = clock64();
 #endif
+        // The WHOLE warp polls the barrier and only the straight-line copy issue below is
+        // lane-0 code: a single lane spinning in a wait loop while the other 31 are parked at the
+        // reconvergence point leaves the warp split for good (measured with __activemask():
+        // lane 0 and lanes 1-31 then run the entire compute phase as two fragments, i.e. the
+        // warp issues every instruction twice -- this, not the producer's work, was the
+        // "2-2.8x slower" of all round-1 producer variants, see tools/ubench_wait.cu).
         mbar_wait(&empty[s], ph ^ 1);
 #ifdef DL_DBGWAIT
         const long long tb = clock64();
         dbg_empty += tb - ta;
 #endif
+        if (DL_ELECT ? elect_one() : lane == 0) {
+#if DL_DISTPROD
+        const int nrows = warp < ROWS ? (ROWS - warp + FW - 1) / FW : 0;
+        if (nrows > 0) mbar_arrive_expect_tx(&full[s], nrows * FZC * sizeof(double));
+        else mbar_arrive(&full[s]);
+        const double* gt = p.grid + (size_t)(t_begin + step) * 2 * p.nB * row + z0;
+        double* dst = stage + s * ROWS * FZC;
+#pragma unroll
+        for (int k = 0; k < (ROWS + FW - 1) / FW; ++k) {
+            const int r = warp + k * FW;
+            if (r < ROWS) {
+                const double* src = r < NF ? gt + (size_t)p.bands[r] * row
+                                  : r < 2 * NF ? gt + (size_t)(p.nB + p.bands[r - NF]) * row
+                                  : p.prior + (size_t)(t_begin + step) * row + z0;
+                tma_bulk_g2s(dst + r * FZC, src, FZC * sizeof(double), &full[s]);
+            }
+        }
+#else
         mbar_arrive_expect_tx(&full[s], ROWS * FZC * sizeof(double));
         const double* gt = p.grid + (size_t)(t_begin + step) * 2 * p.nB * row + z0;
         double* dst = stage + s * ROWS * FZC;
@@ -184,11 +221,14 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
         }
         tma_bulk_g2s(dst + 2 * NF * FZC, p.prior + (size_t)(t_begin + step) * row + z0,
                      FZC * sizeof(double), &full[s]);
+#endif
+        }
+        __syncwarp();
 #ifdef DL_DBGWAIT
         dbg_issue += clock64() - tb;
 #endif
     };
-    if (threadIdx.x == 0) {
+    if (DL_DISTPROD || warp == DL_PRODWARP) {
         for (int step = 0; step < FPREF && step < nsteps; ++step) issue_stage(step);
     }
 
@@ -214,8 +254,8 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
     for (int t = t_begin; t < t_end; ++t, ++it) {
         const int s = it % FSTAGES;
         const uint32_t ph = (it / FSTAGES) & 1;
-        if (threadIdx.x == 0 && it + FPREF < nsteps) issue_stage(it + FPREF);
-        __syncwarp();
+        if ((DL_DISTPROD || warp == DL_PRODWARP) && it + FPREF < nsteps)    // warp-uniform
+            issue_stage(it + FPREF);
 #ifdef DL_DBGWAIT
         const long long tw0 = clock64();
         mbar_wait(&full[s], ph);
@@ -253,9 +293,16 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
                     zoo[c] = zd_sm[2 * FZC + zl + 32 * c]; zev[c] = zd_sm[3 * FZC + zl + 32 * c];
                 }
             }
+#if DL_ROLL_O
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
             for (int o = 0; o < FTO; ++o) {
-                if (DL_ASYM && o == FTO - 1 && nto < FTO) continue;     // warp-uniform
+                // E[] is rotated once per target so the loop can stay rolled with the
+                // accumulators in registers (FTO rotations restore the order)
+                double Eo = E[0];
+                if (!(DL_ASYM && o == FTO - 1 && nto < FTO)) {     // warp-uniform
                 const double* tc = tcw + o * TCS;
                 const double hc = tc[6 * NF + 0], ic = tc[6 * NF + 1];
                 double pOT[ZJ], pTT[ZJ], pOO[ZJ];
@@ -315,6 +362,14 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
                     x[c] = fma(hc, chi2, xmask[c]);              // -chi2/2 in the target's units
                     sarg[c] = x[c] - R;
                 }
+#ifdef DL_DBGWAIT
+                {
+                    bool dead = true;
+#pragma unroll
+                    for (int c = 0; c < ZJ; ++c) dead &= sarg[c] < -708.0;
+                    dbg_div += __all_sync(0xffffffffu, dead);
+                }
+#endif
                 bool up = false;
 #pragma unroll
                 for (int c = 0; c < ZJ; ++c) up |= __double2hiint(sarg[c]) > 0;
@@ -326,7 +381,7 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
                     const double xm = warp_max(xl);
                     if (xm > R) {
                         const double fs = exp(R - xm);
-                        E[o] *= fs;
+                        Eo *= fs;
 #pragma unroll
                         for (int zj = 0; zj < FZT; ++zj) pdfw[o * FZC + zj * 32 + lane] *= fs;
                         __syncwarp();
@@ -360,8 +415,12 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
                 for (int c = 0; c < ZJ; ++c) {
                     const double vp = v[c] * pr[c];
                     pdfw[o * FZC + zl + 32 * c] += vp;
-                    E[o] = fma(vp, wzv[c], E[o]);
+                    Eo = fma(vp, wzv[c], Eo);
                 }
+                }
+#pragma unroll
+                for (int k = 0; k + 1 < FTO; ++k) E[k] = E[k + 1];
+                E[FTO - 1] = Eo;
             }
         }
         // evidence of (target, training galaxy t) over this z-chunk
@@ -385,7 +444,7 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
 #ifdef DL_DBGWAIT
     if (p.dbg && lane == 0) {
         long long* d = p.dbg + ((size_t)(blockIdx.y * gridDim.x + blockIdx.x) * FW + warp) * 4;
-        d[0] = dbg_wait; d[1] = clock64() - dbg_t0; d[2] = dbg_empty; d[3] = dbg_issue;
+        d[0] = dbg_wait; d[1] = clock64() - dbg_t0; d[2] = dbg_empty + dbg_issue; d[3] = dbg_div;
     }
 #endif
 #pragma unroll
@@ -1045,16 +1104,16 @@ int dl_like_fused_dev(long long nO, long long nT, long long nz, long long nB, in
         std::vector<long long> h(dbg_nb * FW * 4);
         cudaStreamSynchronize(stream);
         cudaMemcpy(h.data(), p.dbg, h.size() * 8, cudaMemcpyDeviceToHost);
-        double w[FW] = {0}, tt[FW] = {0}, em = 0, is = 0;
+        double w[FW] = {0}, tt[FW] = {0}, em[FW] = {0}, is[FW] = {0};
         for (size_t b = 0; b < dbg_nb; ++b)
             for (int q = 0; q < FW; ++q) {
                 w[q] += h[(b * FW + q) * 4]; tt[q] += h[(b * FW + q) * 4 + 1];
-                if (q == 0) { em += h[(b * FW) * 4 + 2]; is += h[(b * FW) * 4 + 3]; }
+                em[q] += h[(b * FW + q) * 4 + 2]; is[q] += h[(b * FW + q) * 4 + 3];
             }
-        fprintf(stderr, "[dbgwait] fraction of warp time waiting on TMA data:");
-        for (int q = 0; q < FW; ++q) fprintf(stderr, " w%d=%.3f", q, w[q] / tt[q]);
-        fprintf(stderr, " | producer: empty-wait %.3f issue %.3f | CTA lifetime %.3g cyc\n",
-                em / tt[0], is / tt[0], tt[0] / dbg_nb);
+        fprintf(stderr, "[dbgwait] per warp: full-wait / producer work (fractions of lifetime) / warp-iterations with all 64 cells underflowing, per CTA:");
+        for (int q = 0; q < FW; ++q)
+            fprintf(stderr, " w%d=%.3f/%.3f/%.0f", q, w[q] / tt[q], em[q] / tt[q], is[q] / dbg_nb);
+        fprintf(stderr, " | CTA lifetime %.3g cyc\n", tt[0] / dbg_nb);
     }
 #endif
     if (K > 0) {
