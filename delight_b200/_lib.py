@@ -48,6 +48,8 @@ _SIGS = {
     "dl_zprior_dev": [c_ll, c_ll, c_p, c_p, c_d, c_p, c_p],
     "dl_like_fused_dev": [c_ll, c_ll, c_ll, c_ll, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_d, c_d,
                           c_p, c_p, c_d, c_i, c_i, c_p, c_ll, c_p, c_p, c_p, c_p, c_ll, c_p],
+    "dl_like_compressed_dev": [c_ll, c_ll, c_ll, c_ll, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_d, c_d,
+                               c_p, c_p, c_d, c_i, c_p, c_i, c_p, c_ll, c_p, c_p],
     "dl_metrics_dev": [c_ll, c_ll, c_p, c_ll, c_p, c_p, c_p, c_p],
     "dl_ci_levels_dev": [c_ll, c_ll, c_p, c_ll, c_p, c_i, c_p, c_i, c_p, c_p],
     "dl_gp_fit_dev": [c_ll, c_ll, c_ll, c_ll, c_ll, c_p, c_p, c_p, c_p, c_p, c_p, c_d, c_d, c_p,

@@ -201,6 +201,23 @@ class FusedWorkspace:
         return int(min(tile, (nO + tpc - 1) // tpc * tpc))
 
 
+def _metrics(L, torch, pdf, zg, targets, confidence_levels):
+    """computeMetrics on device (utils.py:213-227): 7 + nCL columns followed by the argmax index."""
+    nO, nz = pdf.shape
+    zt = _as_dev(targets.ztrue) if targets.ztrue is not None else None
+    metrics = torch.empty((nO, 8), dtype=torch.float64, device="cuda")
+    _lib.check(L.dl_metrics_dev(nO, nz, _lib.ptr(pdf), nz, _lib.ptr(zg), _lib.ptr(zt),
+                                _lib.ptr(metrics), _lib.stream_ptr()))
+    if confidence_levels is not None and len(confidence_levels):
+        # computeMetrics: CIlevel(grid, PDF, 1.0 - confI) per level  (utils.py:223-225)
+        fr = _as_dev(1.0 - np.asarray(confidence_levels, dtype=np.float64))
+        ci = torch.empty((nO, fr.numel()), dtype=torch.float64, device="cuda")
+        _lib.check(L.dl_ci_levels_dev(nO, nz, _lib.ptr(pdf), nz, _lib.ptr(zg), fr.numel(),
+                                      _lib.ptr(fr), 200, _lib.ptr(ci), _lib.stream_ptr()))
+        metrics = torch.cat([metrics[:, :7], ci, metrics[:, 7:]], dim=1)
+    return metrics
+
+
 def apply_fused(grid, prior, zgrid, targets, ell_hat=1.0, ell_var=1.0, K=0, want_evid=False,
                 want_metrics=False, workspace=None, nsplit=None, out_device=False,
                 confidence_levels=None, cov_scale=1.0):
@@ -301,21 +318,86 @@ def apply_fused(grid, prior, zgrid, targets, ell_hat=1.0, ell_var=1.0, K=0, want
             if want_evid:
                 evid.index_copy_(0, didx, g_evid)
 
-    metrics = None
-    if want_metrics:
-        zt = _as_dev(targets.ztrue) if targets.ztrue is not None else None
-        metrics = torch.empty((nO, 8), dtype=torch.float64, device="cuda")
-        _lib.check(L.dl_metrics_dev(nO, nz, _lib.ptr(pdf), nz, _lib.ptr(zg), _lib.ptr(zt),
-                                    _lib.ptr(metrics), _lib.stream_ptr()))
-        if confidence_levels is not None and len(confidence_levels):
-            # computeMetrics: CIlevel(grid, PDF, 1.0 - confI) per level  (utils.py:223-225)
-            fr = _as_dev(1.0 - np.asarray(confidence_levels, dtype=np.float64))
-            ci = torch.empty((nO, fr.numel()), dtype=torch.float64, device="cuda")
-            _lib.check(L.dl_ci_levels_dev(nO, nz, _lib.ptr(pdf), nz, _lib.ptr(zg), fr.numel(),
-                                          _lib.ptr(fr), 200, _lib.ptr(ci), _lib.stream_ptr()))
-            metrics = torch.cat([metrics[:, :7], ci, metrics[:, 7:]], dim=1)
+    metrics = _metrics(L, torch, pdf, zg, targets, confidence_levels) if want_metrics else None
     out = dict(pdf=pdf, top_idx=top_idx, top_ev=top_ev, evid=evid, metrics=metrics,
                fused_launches=launches)
+    if not out_device:
+        for k, v in list(out.items()):
+            if isinstance(v, torch.Tensor):
+                out[k] = v.cpu().numpy()
+    return out
+
+
+def apply_compressed(grid, prior, zgrid, targets, indices, ell_hat=1.0, ell_var=1.0,
+                     normalized=False, want_metrics=False, confidence_levels=None,
+                     cov_scale=1.0, out_device=False):
+    """Second ("compressed") pass of delight-apply.py:109-135: every target is compared only with
+    the training galaxies whose indices the first pass stored (`indices` [nO, K], the rows of
+    compressIndicesFile).  Likelihood = the reference's NumPy twin utils.py:115-176 with
+    marginalizeEll / renormalize and `normalized` as given (the script passes False), times the
+    prior; pdf = sum over the selected galaxies (:145), evidences = trapz_z (:146).
+
+    Like `np.in1d(targetIndices, indices)` (:125) the selection is a set: duplicates count once,
+    entries that are no training index are ignored, columns are taken in ascending index order.
+    Returns dict(pdf [nO, nz], sel [nO, K] int64 (ascending, -1 padded), evid [nO, K] (aligned
+    with sel), metrics | None).
+    """
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    nO = len(targets)
+    nT, nB, nz = grid.nT, grid.nB, grid.nz
+    indices = np.asarray(indices)
+    if indices.ndim != 2 or indices.shape[0] != nO:
+        raise ValueError("indices must be [n_targets, K]")
+    if not np.issubdtype(indices.dtype, np.integer):
+        raise ValueError("indices must be integers")
+    K = indices.shape[1]
+    if K < 1:
+        raise ValueError("need at least one stored index per target")
+    if targets.fluxes.shape[1] > nB and targets.bands.max() >= nB:
+        raise ValueError("target band index outside the model grid")
+    # the in1d mask as a sorted, de-duplicated, -1 padded index list per target
+    big = np.iinfo(np.int64).max
+    sel = np.where((indices >= 0) & (indices < nT), indices, big).astype(np.int64)
+    sel.sort(axis=1)
+    dup = np.zeros_like(sel, dtype=bool)
+    dup[:, 1:] = sel[:, 1:] == sel[:, :-1]
+    sel[dup] = big
+    sel.sort(axis=1)
+    sel[sel == big] = -1
+    zg = _as_dev(zgrid)
+    zdep = np.ndim(ell_hat) > 0 or np.ndim(ell_var) > 0
+    if zdep:
+        eh = _as_dev(np.broadcast_to(np.asarray(ell_hat, dtype=np.float64), (nz,)))
+        ev = _as_dev(np.broadcast_to(np.asarray(ell_var, dtype=np.float64), (nz,)))
+        ehs = evs = 1.0
+    else:
+        eh = ev = None
+        ehs, evs = float(ell_hat), float(ell_var)
+    pdf = torch.empty((nO, nz), dtype=torch.float64, device="cuda")
+    evid = torch.zeros((nO, K), dtype=torch.float64, device="cuda")
+    sel_d = torch.from_numpy(sel).cuda()
+    for bands, idx in (targets.groups() if nO else []):
+        nf = len(bands)
+        single = idx.size == nO
+        obs = torch.from_numpy(np.ascontiguousarray(targets.fluxes[idx, :nf])).cuda()
+        var = torch.from_numpy(np.ascontiguousarray(targets.fluxes_var[idx, :nf])).cuda()
+        didx = None if single else torch.from_numpy(idx).cuda()
+        g_sel = sel_d if single else sel_d.index_select(0, didx).contiguous()
+        g_pdf = pdf if single else torch.empty((idx.size, nz), dtype=torch.float64, device="cuda")
+        g_ev = evid if single else torch.empty((idx.size, K), dtype=torch.float64, device="cuda")
+        bands_c = (ctypes.c_int * nf)(*bands)
+        _lib.check(L.dl_like_compressed_dev(
+            idx.size, nT, nz, nB, nf, bands_c, _lib.ptr(obs), _lib.ptr(var), _lib.ptr(grid.grid),
+            _lib.ptr(prior), _lib.ptr(zg), ehs, evs, _lib.ptr(eh), _lib.ptr(ev), float(cov_scale),
+            K, _lib.ptr(g_sel), int(bool(normalized)), _lib.ptr(g_pdf), nz, _lib.ptr(g_ev),
+            _lib.stream_ptr()))
+        if not single:
+            pdf.index_copy_(0, didx, g_pdf)
+            evid.index_copy_(0, didx, g_ev)
+    metrics = _metrics(L, torch, pdf, zg, targets, confidence_levels) \
+        if want_metrics and nO else None
+    out = dict(pdf=pdf, sel=sel_d, evid=evid, metrics=metrics)
     if not out_device:
         for k, v in list(out.items()):
             if isinstance(v, torch.Tensor):

@@ -177,8 +177,7 @@ def apply(cfg_path, write=True, cap_training_like_reference=True):
     if p["training_numChunks"] != 1:
         raise NotImplementedError("numChunks > 1 normalises each chunk separately in the "
                                   "reference (SURVEY appendix A); only numChunks = 1")
-    if p["useCompression"] and p["compressionFilesFound"]:
-        raise NotImplementedError("second (compressed) pass is not implemented")
+    compressed = p["useCompression"] and p["compressionFilesFound"]     # delight-apply.py:109
     rank, size = _dist.init()
     import torch
     gpm, zgrid = make_gp(p)
@@ -197,9 +196,18 @@ def apply(cfg_path, write=True, cap_training_like_reference=True):
     K = p["Ncompress"]
     ncl = len(p["confidenceLevels"])
     with_z = "redshift" in p["target_bandOrder"]
-    res = _apply.apply_fused(grid, prior, zgrid, targets, ell_hat=1.0,
-                             ell_var=p["ellPriorSigma"] ** 2, K=K, want_metrics=with_z,
-                             confidence_levels=p["confidenceLevels"], out_device=True)
+    if compressed:
+        # second pass: only the training galaxies stored by the first one (:123-135)
+        stored = np.atleast_2d(_load(p["compressIndicesFile"]))[first:last].astype(np.int64)
+        res = _apply.apply_compressed(grid, prior, zgrid, targets, stored[:len(targets)],
+                                      ell_hat=1.0, ell_var=p["ellPriorSigma"] ** 2,
+                                      normalized=False, want_metrics=with_z,
+                                      confidence_levels=p["confidenceLevels"], out_device=True)
+        res["top_idx"], res["top_ev"] = res["sel"], res["evid"]
+    else:
+        res = _apply.apply_fused(grid, prior, zgrid, targets, ell_hat=1.0,
+                                 ell_var=p["ellPriorSigma"] ** 2, K=K, want_metrics=with_z,
+                                 confidence_levels=p["confidenceLevels"], out_device=True)
 
     def full(a, width, dt=torch.float64):
         out = torch.zeros((n_lines, width), dtype=dt, device="cuda")

@@ -152,6 +152,22 @@ int dl_like_fused_dev(long long nO, long long nT, long long nz, long long nB, in
                       double* evid, long long* top_idx, double* top_ev, void* workspace,
                       long long workspace_bytes, void* stream);
 
+/* Compressed second pass               replaces scripts/delight-apply.py:109-135,145-146 x nO
+ * (useCompression with the compressIndices file of a first pass present): per target only the K
+ * stored training galaxies sel[o][0..K) (device, int64; entries outside [0, nT) are skipped)
+ * enter the likelihood, which is the NumPy twin delight/utils.py:115-176 with
+ * marginalizeEll=True, renormalize=True and `normalized` as given (the script passes False: no
+ * log-determinant terms); like *= prior; pdf = sum over the selected galaxies;
+ * evid[o][k] = trapz_z of column sel[o][k] (0 for skipped entries; may be NULL).
+ * Same grid / prior layout and band-group convention as dl_like_fused_dev; nf <= 64. */
+int dl_like_compressed_dev(long long nO, long long nT, long long nz, long long nB, int nf,
+                           const int* bands, const double* obs, const double* var,
+                           const double* grid, const double* prior, const double* zgrid,
+                           double ell_hat, double ell_var, const double* ell_hat_z,
+                           const double* ell_var_z, double cov_scale, int K,
+                           const long long* sel, int normalized, double* pdf, long long ld_pdf,
+                           double* evid, void* stream);
+
 /* computeMetrics core                  replaces delight/utils.py:213-227 (first 7 columns)
  * out [nO][8]: ztrue zmean std(zmean) zMAP std(zMAP) pdf(ztrue) cumpdf(ztrue) argmax-index */
 int dl_metrics_dev(long long nO, long long nz, const double* pdf, long long ld_pdf,

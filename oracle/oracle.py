@@ -99,6 +99,74 @@ def apply_fused(fluxes, fluxes_var, nf, bands, model_mean, model_covar, prior, z
 
 
 # ------------------------------------------------------------------------------------------------
+# compressed second pass  (scripts/delight-apply.py:109-135,145-147; delight/utils.py:115-176)
+# ------------------------------------------------------------------------------------------------
+def flux_like_twin(f_obs, f_obs_var, f_mod, f_mod_covar, ell_hat, ell_var, normalized):
+    """delight.utils.approx_flux_likelihood (utils.py:115-176) for the call the compressed branch
+    makes: 3-D covariance (two iterations), marginalizeEll=True, renormalize=True, all
+    ell_var > 0.  ell_hat / ell_var: scalars or [nz] arrays (broadcast over training galaxies).
+    `normalized` switches the log-determinant terms (:165-168); delight-apply.py:131 passes False.
+    Returns like[nz, nt] = exp(L - max L)."""
+    f_obs = np.asarray(f_obs, dtype=np.float64)
+    f_obs_var = np.asarray(f_obs_var, dtype=np.float64)
+    nz, nt, nf = f_mod.shape
+    eh = np.broadcast_to(np.asarray(ell_hat, dtype=np.float64), (nz,))[:, None]
+    ev = np.broadcast_to(np.asarray(ell_var, dtype=np.float64), (nz,))[:, None]
+    assert np.all(ev > 0)
+    ellML = 0.0
+    for _ in range(2):                                                    # utils.py:141-160
+        var = f_obs_var[None, None, :] + ellML ** 2 * f_mod_covar
+        invvar = 1.0 / var
+        FOT = np.sum(f_mod * f_obs[None, None, :] * invvar, axis=2) + eh / ev
+        FTT = np.sum(f_mod ** 2 * invvar, axis=2) + 1.0 / ev
+        FOO = np.sum(f_obs[None, None, :] ** 2 * invvar, axis=2) + eh ** 2 / ev
+        log_sigma_det = np.sum(np.log(var), axis=2)
+        ellML = (FOT / FTT)[:, :, None]
+    chi2 = FOO - FOT ** 2 / FTT                                           # :163
+    logDenom = 0.0
+    if normalized:                                                        # :167-170
+        logDenom = logDenom + log_sigma_det + nf * np.log(2 * np.pi) + np.log(2 * np.pi * ev)
+    logDenom = logDenom + np.log(FTT) - np.log(2 * np.pi)                 # :171-174
+    like = -0.5 * chi2 - 0.5 * logDenom
+    like -= like.max()                                                    # :175-176
+    return np.exp(like)
+
+
+def apply_compressed(fluxes, fluxes_var, nf, bands, model_mean, model_covar, prior, zgrid,
+                     ell_hat, ell_var, indices, normalized=False):
+    """The second ("compressed") pass of delight-apply.py:109-135 as its author evidently meant
+    it: per target only the training galaxies whose indices were stored by the first pass
+    (compressIndicesFile) enter the likelihood.  The reference assigns the result to
+    `like_grid2` and then keeps using the stale `like_grid` (:126,:135) and hands 1-D [nz]
+    ell arrays to the NumPy twin, which cannot broadcast them against [nz, K]; this restatement
+    uses the computed array and broadcasts ell over the training-galaxy axis.
+    `sel = np.in1d(targetIndices, indices)` (:125) is a mask, so the selected columns come in
+    ascending training index order, each once.
+    indices: [nO, K] int (entries outside [0, nT) are ignored, like the mask does).
+    Returns dict(pdf [nO, nz], sel list of index arrays, evid list of [len(sel)] arrays)."""
+    nz, nT, nB = model_mean.shape
+    nO = fluxes.shape[0]
+    pdf = np.zeros((nO, nz))
+    sels, evids = [], []
+    for o in range(nO):
+        b = np.asarray(bands[o, :nf[o]], dtype=np.int64)
+        sel = np.unique(indices[o][(indices[o] >= 0) & (indices[o] < nT)])
+        if sel.size == 0:          # nothing stored (the reference would fail on like.max())
+            sels.append(sel)
+            evids.append(np.zeros(0))
+            continue
+        like = flux_like_twin(fluxes[o, :nf[o]], fluxes_var[o, :nf[o]],
+                              model_mean[:, sel, :][:, :, b], model_covar[:, sel, :][:, :, b],
+                              ell_hat, ell_var, normalized)
+        like = like * prior[:, sel]                                       # :135
+        pdf[o] = like.sum(axis=1)                                         # :145
+        evids.append(np.trapezoid(like, x=zgrid, axis=0) if hasattr(np, 'trapezoid')
+                     else np.trapz(like, x=zgrid, axis=0))                     # :146
+        sels.append(sel)
+    return dict(pdf=pdf, sel=sels, evid=evids)
+
+
+# ------------------------------------------------------------------------------------------------
 # GP kernel pieces  (delight/photoz_kernels_cy.pyx)
 # ------------------------------------------------------------------------------------------------
 def kernelparts(NO1, NO2, NC, NL, alpha_C, alpha_L, fcoefs_amp, fcoefs_mu, fcoefs_sig,

@@ -13,6 +13,8 @@ Writes
     tests/golden/sdss_pipeline.npz     seeded mock -> reference learn -> predict -> apply epilogue
                                        (5 SDSS bands, training on 3, heterogeneous targets)
     tests/golden/templatefit.npz       templateFitting.py-equivalent (config 2 twin)
+    tests/golden/compressed_small.npz  second ("compressed") pass of delight-apply.py:123-135:
+                                       the reference's NumPy twin on the stored top-K columns
     delight_b200/data/lsst_cww.npz     LSST ugrizy Gaussian coefficients + CWW template flux
                                        tables on the 1500-point z grid (outputs of the
                                        reference's processFilters/processSEDs), used by bench.py
@@ -71,6 +73,60 @@ def gen_like_small():
     np.savez_compressed(os.path.join(GOLD, "like_small.npz"), **out)
     print("like_small: max |cy/twin-1| =",
           max(np.abs(out[c[0] + "_like"] / out[c[0] + "_twin"] - 1).max() for c in cases))
+
+
+def gen_compressed_small():
+    """delight-apply.py:123-135,145-146 with the computed array actually used (the script keeps
+    the stale `like_grid`) and ell broadcast over the training axis (the script's 1-D arrays do
+    not broadcast against [nz, K])."""
+    from delight.utils import approx_flux_likelihood
+    rng = np.random.default_rng(4321)
+    nz, nT, nB, nO, K = 40, 30, 5, 6, 8
+    zgrid = np.sort(rng.uniform(0.01, 3.0, nz))
+    model_mean = rng.uniform(0.5, 2, (nz, nT, nB)) * 1e5 * rng.uniform(.1, 10, (1, nT, 1))
+    model_covar = (model_mean * rng.uniform(1e-4, 1e-2, (nz, nT, nB))) ** 2
+    train_z = rng.uniform(0.01, 3.0, nT)
+    prior = np.exp(-0.5 * ((zgrid[:, None] - train_z[None, :]) / 0.5) ** 2)
+    nf = np.array([5, 5, 3, 4, 2, 5])
+    bands = np.zeros((nO, nB), dtype=np.int64)
+    fluxes = np.zeros((nO, nB))
+    fluxes_var = np.ones((nO, nB))
+    for o in range(nO):
+        b = np.sort(rng.choice(nB, nf[o], replace=False))
+        bands[o, :nf[o]] = b
+        t, iz = rng.integers(nT), rng.integers(nz)
+        f = model_mean[iz, t, b] * 4e-10 * rng.uniform(0.9, 1.1, nf[o])
+        fluxes[o, :nf[o]] = f
+        fluxes_var[o, :nf[o]] = (0.05 * f) ** 2
+    indices = np.stack([rng.choice(nT, K, replace=False) for _ in range(nO)]).astype(np.int64)
+    indices[1, 3] = indices[1, 0]          # duplicate entry: the in1d mask keeps one column
+    indices[2, 5] = nT + 7                 # not a training index: ignored by the mask
+    ell_hat = rng.uniform(.5, 2, nz)
+    ell_var = rng.uniform(.1, .5, nz)
+    out = dict(zgrid=zgrid, model_mean=model_mean, model_covar=model_covar, prior=prior, nf=nf,
+               bands=bands, fluxes=fluxes, fluxes_var=fluxes_var, indices=indices,
+               ell_hat=ell_hat, ell_var=ell_var)
+    targetIndices = np.arange(nT)
+    for tag, normalized, eh, ev in (("n0", False, ell_hat, ell_var), ("n1", True, ell_hat, ell_var),
+                                    ("s0", False, np.ones(nz), np.full(nz, 0.25))):
+        pdfs = np.zeros((nO, nz))
+        evid = np.zeros((nO, K))
+        sel_sorted = -np.ones((nO, K), dtype=np.int64)
+        for o in range(nO):
+            b = bands[o, :nf[o]]
+            sel = np.in1d(targetIndices, indices[o], assume_unique=True)       # :125
+            like_grid = approx_flux_likelihood(                                 # :126-134
+                fluxes[o, :nf[o]], fluxes_var[o, :nf[o]], model_mean[:, sel, :][:, :, b],
+                f_mod_covar=model_covar[:, sel, :][:, :, b], marginalizeEll=True,
+                normalized=normalized, ell_hat=eh[:, None], ell_var=ev[:, None])
+            like_grid *= prior[:, sel]                                          # :135
+            pdfs[o] = like_grid.sum(axis=1)                                     # :145
+            e = np.trapz(like_grid, x=zgrid, axis=0)                            # :146
+            evid[o, :e.size] = e
+            sel_sorted[o, :e.size] = targetIndices[sel]
+        out["pdf_" + tag], out["evid_" + tag], out["sel_" + tag] = pdfs, evid, sel_sorted
+    np.savez_compressed(os.path.join(GOLD, "compressed_small.npz"), **out)
+    print("compressed_small done")
 
 
 def gen_kernelparts_small(amp, mu, sig):
@@ -373,9 +429,11 @@ def gen_lsst_data(wd):
 if __name__ == "__main__":
     ref.load()
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["like", "sdss", "lsst"]
+    which = sys.argv[1:] or ["like", "comp", "sdss", "lsst"]
     if "like" in which:
         gen_like_small()
+    if "comp" in which:
+        gen_compressed_small()
     if "sdss" in which:
         with tempfile.TemporaryDirectory(prefix="delight_gold_") as wd:
             amp, mu, sig = gen_sdss_pipeline(wd)

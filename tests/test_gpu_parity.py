@@ -802,3 +802,93 @@ def test_cov_scale_and_sweep(orc, sdss, tmp_path):
     np.testing.assert_allclose(sw[key], out["metrics"][:n], rtol=1e-9)
     other = sw[(float(g["ellPriorSigma"]), 0.1, 0.1)]
     assert other.shape == sw[key].shape and not np.allclose(other[:, 1], sw[key][:, 1])
+
+
+# ------------------------------------------------------------------------------------------------
+# compressed second pass  (delight-apply.py:109-135)
+# ------------------------------------------------------------------------------------------------
+def test_compressed_pass_golden(golden):
+    """dl_like_compressed_dev vs the reference's NumPy twin on the stored columns."""
+    from delight_b200 import apply
+    g = golden("compressed_small")
+    grid = apply.ModelGrid.from_legacy(g["model_mean"], g["model_covar"])
+    prior = grid.explicit_prior(g["prior"])
+    t = apply.Targets(g["fluxes"], g["fluxes_var"], g["bands"], g["nf"], None)
+    for tag, norm, eh, ev in (("n0", False, g["ell_hat"], g["ell_var"]),
+                              ("n1", True, g["ell_hat"], g["ell_var"]), ("s0", False, 1.0, 0.25)):
+        r = apply.apply_compressed(grid, prior, g["zgrid"], t, g["indices"], ell_hat=eh,
+                                   ell_var=ev, normalized=norm)
+        np.testing.assert_array_equal(r["sel"], g["sel_" + tag])
+        np.testing.assert_allclose(r["pdf"], g["pdf_" + tag], rtol=RTOL,
+                                   atol=1e-290 * g["pdf_" + tag].max())
+        np.testing.assert_allclose(r["evid"], g["evid_" + tag], rtol=RTOL,
+                                   atol=1e-290 * g["evid_" + tag].max())
+
+
+def test_compressed_pass_random_vs_oracle(orc):
+    """Larger ragged case (nz not a multiple of the chunk, K > number of distinct indices, a
+    target whose stored list is empty) against the oracle."""
+    from delight_b200 import apply
+    rng = np.random.default_rng(99)
+    nz, nT, nB, nO, K = 301, 120, 6, 37, 16
+    zgrid = np.linspace(0.01, 3.0, nz)
+    mm = rng.uniform(0.5, 2, (nz, nT, nB)) * 1e5 * rng.uniform(.1, 10, (1, nT, 1))
+    mc = (mm * rng.uniform(1e-4, 1e-2, (nz, nT, nB))) ** 2
+    prior = np.exp(-0.5 * ((zgrid[:, None] - rng.uniform(0, 3, nT)[None, :]) / 0.5) ** 2)
+    nf = rng.integers(2, nB + 1, nO)
+    bands = np.zeros((nO, nB), dtype=np.int64)
+    fl, fv = np.zeros((nO, nB)), np.ones((nO, nB))
+    for o in range(nO):
+        b = np.sort(rng.choice(nB, nf[o], replace=False))
+        bands[o, :nf[o]] = b
+        f = mm[rng.integers(nz), rng.integers(nT), b] * 4e-10 * rng.uniform(0.9, 1.1, nf[o])
+        fl[o, :nf[o]], fv[o, :nf[o]] = f, (0.05 * f) ** 2
+    idx = rng.integers(0, nT, (nO, K))
+    idx[3] = -1                                   # nothing stored for this target
+    want = orc.apply_compressed(fl, fv, nf, bands, mm, mc, prior, zgrid, 1.0, 0.25, idx)
+    grid = apply.ModelGrid.from_legacy(mm, mc)
+    got = apply.apply_compressed(grid, grid.explicit_prior(prior), zgrid,
+                                 apply.Targets(fl, fv, bands, nf, None), idx, ell_hat=1.0,
+                                 ell_var=0.25)
+    for o in range(nO):
+        n = want["sel"][o].size
+        np.testing.assert_array_equal(got["sel"][o, :n], want["sel"][o])
+        assert np.all(got["sel"][o, n:] == -1) and np.all(got["evid"][o, n:] == 0)
+        if n == 0:
+            assert np.all(got["pdf"][o] == 0)
+            continue
+        np.testing.assert_allclose(got["pdf"][o], want["pdf"][o], rtol=RTOL,
+                                   atol=1e-290 * want["pdf"][o].max())
+        np.testing.assert_allclose(got["evid"][o, :n], want["evid"][o], rtol=RTOL,
+                                   atol=1e-290 * want["evid"][o].max())
+
+
+def test_pipeline_second_pass_uses_stored_indices(orc, sdss, tmp_path):
+    """pipeline.apply twice on one cfg: the first pass writes compressIndices / compressLikes,
+    the second finds them (delight-apply.py:109) and only uses those training galaxies."""
+    from oracle import pipeline as refpipe
+    from delight_b200 import pipeline
+    g = sdss
+    wd = str(tmp_path)
+    K = int(g["Ncompress"])
+    cfg = refpipe.make_workdir(wd, bands=refpipe.SDSS,
+                               train_bands=["U_SDSS", "G_SDSS", "I_SDSS"], refband="I_SDSS",
+                               numObjects=24, dz=0.01, nzGP=40, Ncompress=K, copy_data=False)
+    refpipe.write_preprocessed(wd, refpipe.SDSS, g["amp"], g["mu"], g["sig"], g["tmpl"])
+    np.savetxt(wd + "/galaxies-fluxredshifts.txt", g["train_cat"])
+    np.savetxt(wd + "/galaxies-fluxredshifts2.txt", g["target_cat"])
+    pipeline.learn(cfg)
+    first = pipeline.apply(cfg)
+    second = pipeline.apply(cfg)
+    n = g["pdfs"].shape[0]
+    want = orc.apply_compressed(g["ta_flux"], g["ta_var"], g["ta_nb"], g["ta_bands"],
+                                g["model_mean"], g["model_covar"], g["prior"], g["zgrid"], 1.0,
+                                float(g["ellPriorSigma"]) ** 2, first["top_idx"][:n])
+    np.testing.assert_allclose(second["pdfs"][:n], want["pdf"], rtol=1e-6,
+                               atol=1e-290 * want["pdf"].max())
+    # the K best training galaxies carry nearly all of the posterior mass: the compressed PDFs
+    # follow the full ones once both are normalised
+    a = second["pdfs"][:n] / second["pdfs"][:n].sum(axis=1, keepdims=True)
+    b = first["pdfs"][:n] / first["pdfs"][:n].sum(axis=1, keepdims=True)
+    assert np.abs(a - b).max() < 0.05 * b.max()
+    assert second["metrics"].shape == first["metrics"].shape

@@ -178,3 +178,24 @@ def test_templatefit_twin(golden):
     np.testing.assert_allclose(res["pdf"], g["pdfs"], rtol=1e-10, atol=1e-300)
     np.testing.assert_allclose(orc.template_prior(s["zgrid"], g["p_t"], g["p_z_t"]), g["p_z"],
                                rtol=1e-14)
+
+
+def test_compressed_second_pass_matches_reference_twin(golden):
+    """oracle.apply_compressed vs the reference's NumPy twin run on the stored columns
+    (tests/golden/make_golden.py:gen_compressed_small; delight-apply.py:123-135,145-146)."""
+    g = golden("compressed_small")
+    nO = g["fluxes"].shape[0]
+    for tag, norm, eh, ev in (("n0", False, g["ell_hat"], g["ell_var"]),
+                              ("n1", True, g["ell_hat"], g["ell_var"]), ("s0", False, 1.0, 0.25)):
+        r = orc.apply_compressed(g["fluxes"], g["fluxes_var"], g["nf"], g["bands"],
+                                 g["model_mean"], g["model_covar"], g["prior"], g["zgrid"],
+                                 eh, ev, g["indices"], normalized=norm)
+        np.testing.assert_allclose(r["pdf"], g["pdf_" + tag], rtol=1e-13)
+        for o in range(nO):
+            n = r["sel"][o].size
+            np.testing.assert_array_equal(r["sel"][o], g["sel_" + tag][o, :n])
+            assert np.all(g["sel_" + tag][o, n:] == -1)
+            np.testing.assert_allclose(r["evid"][o], g["evid_" + tag][o, :n], rtol=1e-13)
+    # duplicate and out-of-range stored indices select fewer columns
+    assert (g["sel_n0"][1] >= 0).sum() == g["indices"].shape[1] - 1
+    assert (g["sel_n0"][2] >= 0).sum() == g["indices"].shape[1] - 1
