@@ -90,12 +90,28 @@ constexpr int FPREF = DL_PREF;      // prefetch distance in steps (< FSTAGES)
 #ifndef DL_ELECT
 #define DL_ELECT 1
 #endif
+
+
 constexpr int FTPC = FW * FTO - DL_ASYM;    // targets per CTA
 constexpr int FTHREADS = FW * 32;
 constexpr int MAXNF = 16;
 
 // per-target constants: [f][2] = (a', w') | [f][4] = (var', obs, obs^2, 0) | hc ic pOT pTT pOO c
 __host__ __device__ constexpr int tc_stride(int nf) { return 6 * nf + 6; }
+
+// Shared memory of one CTA with a ring of `stages`, and the ring depth used for NF bands: the
+// deepest ring up to DL_STAGES (at least 2) that still lets two CTAs share an SM
+// (228 KB per SM, 1 KB reserved per CTA); beyond 13 bands only one CTA fits anyway.
+__host__ __device__ constexpr size_t fused_smem_bytes(int nf, bool zdep, int stages) {
+    return sizeof(double) * ((size_t)stages * (2 * nf + 1) * FZC + FTPC * FZC + FTPC * tc_stride(nf) +
+                             FTPC * 2 + FZC + (zdep ? 4 * FZC : 0)) + 2 * stages * sizeof(uint64_t);
+}
+__host__ __device__ constexpr int fused_stages(int nf, bool zdep) {
+    int s = FSTAGES;
+    while (s > 2 && 2 * (fused_smem_bytes(nf, zdep, s) + 1024) > 228 * 1024) --s;
+    if (2 * (fused_smem_bytes(nf, zdep, s) + 1024) > 228 * 1024) s = FSTAGES;   // one CTA per SM
+    return s;
+}
 
 struct FusedParams {
     const double* grid;    // [nT][2*nB][nzp]  rows 0..nB-1 mean, nB..2nB-1 variance
@@ -112,19 +128,77 @@ struct FusedParams {
     long long* dbg;        // DL_DBGWAIT builds: [grid][FW][4] cycle counters
 };
 
+// x = -chi2/2 (in the target's units, + the padding mask) and y = (det)^-1/2 of ZJ cells of one
+// target against one training galaxy: utils_cy.pyx:98-118 restructured (see the header comment).
+// tc: the target's constants, m / cv: band means / variances of the cells.
+template <int NF, int ZJ>
+__device__ __forceinline__ void cells_xy(const double* tc, const double (&m)[ZJ][NF],
+                                         const double (&cv)[ZJ][NF], const double (&pOT)[ZJ],
+                                         const double (&pTT)[ZJ], const double (&pOO)[ZJ],
+                                         const double (&zev)[ZJ], const double (&xmask)[ZJ],
+                                         double (&x)[ZJ], double (&y)[ZJ]) {
+    const double hc = tc[6 * NF + 0], ic = tc[6 * NF + 1];
+    // pass 0: observed variances only (utils_cy.pyx:101-113 with ellML = 0)
+    double fot[ZJ], ftt[ZJ], foo[ZJ], P[ZJ], e2[ZJ];
+#pragma unroll
+    for (int c = 0; c < ZJ; ++c) { fot[c] = pOT[c]; ftt[c] = pTT[c]; }
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        const double a = tc[2 * f], w = tc[2 * f + 1];
+#pragma unroll
+        for (int c = 0; c < ZJ; ++c) {
+            const double tw = m[c][f] * w;
+            fot[c] = fma(m[c][f], a, fot[c]);
+            ftt[c] = fma(tw, m[c][f], ftt[c]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < ZJ; ++c) {
+        const double ell = fot[c] * rcp_fast(ftt[c]);
+        e2[c] = ell * (ell * ic);
+        fot[c] = pOT[c]; ftt[c] = pTT[c]; foo[c] = pOO[c]; P[c] = zev[c];
+    }
+    // pass 1: variance inflated by ell^2 * model variance (utils_cy.pyx:107-112)
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        const double ov = tc[2 * NF + 4 * f], ob = tc[2 * NF + 4 * f + 1],
+                     o2 = tc[2 * NF + 4 * f + 2];
+#pragma unroll
+        for (int c = 0; c < ZJ; ++c) {
+            const double var = fma(e2[c], cv[c][f], ov);
+            const double r = rcp_fast(var);
+            const double tm = m[c][f] * r;
+            fot[c] = fma(tm, ob, fot[c]);
+            ftt[c] = fma(tm, m[c][f], ftt[c]);
+            foo[c] = fma(o2, r, foo[c]);
+            P[c] *= var;
+        }
+    }
+    // chi2 and (det)^-1/2 (utils_cy.pyx:111-118)
+#pragma unroll
+    for (int c = 0; c < ZJ; ++c) {
+        y[c] = rsqrt_fast(P[c] * ftt[c]);
+        const double rF = (y[c] * y[c]) * P[c];      // 1 / FTT
+        const double chi2 = fma(-(fot[c] * rF), fot[c], foo[c]);
+        x[c] = fma(hc, chi2, xmask[c]);              // -chi2/2 in the target's units
+    }
+}
+
 template <int NF, bool ZDEP, int ZJ>
 __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const FusedParams p) {
     constexpr int ROWS = 2 * NF + 1;
     constexpr int TCS = tc_stride(NF);
+    constexpr int STG = fused_stages(NF, ZDEP);                 // ring depth
+    constexpr int PREF = (FPREF < STG - 2 ? FPREF : STG - 2) > 1 ? (FPREF < STG - 2 ? FPREF : STG - 2) : 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* stage = reinterpret_cast<double*>(smem_raw);        // [FSTAGES][ROWS][FZC]
-    double* pdf_sm = stage + FSTAGES * ROWS * FZC;              // [FTPC][FZC]
+    double* stage = reinterpret_cast<double*>(smem_raw);        // [STG][ROWS][FZC]
+    double* pdf_sm = stage + STG * ROWS * FZC;              // [FTPC][FZC]
     double* tc_sm = pdf_sm + FTPC * FZC;                        // [FTPC][TCS]
     double* rv_sm = tc_sm + FTPC * TCS;                         // [FTPC][2]  (R, V) per target
     double* wz_sm = rv_sm + FTPC * 2;                           // [FZC]
     double* zd_sm = wz_sm + FZC;                                // [4][FZC] (ZDEP only)
     uint64_t* full = reinterpret_cast<uint64_t*>(zd_sm + (ZDEP ? 4 * FZC : 0));
-    uint64_t* empty = full + FSTAGES;
+    uint64_t* empty = full + STG;
 
     // Target tile fastest, z-chunk slowest: the ~300 CTAs resident at any time then work on at
     // most two z-chunks, i.e. they stream the SAME 13-row x 128-redshift slices of the model
@@ -142,7 +216,7 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
     const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < FSTAGES; ++s) {
+        for (int s = 0; s < STG; ++s) {
             mbar_init(&full[s], DL_DISTPROD ? FW : 1);
             mbar_init(&empty[s], FW);
         }
@@ -166,7 +240,7 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
 
     // ---------------------------------------------------------------------- TMA producer
     // No dedicated producer warp (it would cost 32 registers/thread of occupancy): warp 0
-    // refills, before it computes step `it`, the stage every warp released FPREF steps ago.
+    // refills, before it computes step `it`, the stage every warp released PREF steps ago.
     // (Measured alternatives: deeper rings 3-6 % slower; prefetch distance 1 or 3 no change.)
     const int nsteps = t_end - t_begin;
 #ifdef DL_DBGWAIT
@@ -174,8 +248,8 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
     const long long dbg_t0 = clock64();
 #endif
     auto issue_stage = [&](int step) {
-        const int s = step % FSTAGES;
-        const uint32_t ph = (step / FSTAGES) & 1;
+        const int s = step % STG;
+        const uint32_t ph = (step / STG) & 1;
         const size_t row = (size_t)p.nzp;
 #ifdef DL_DBGWAIT
         const long long ta = clock64();
@@ -229,7 +303,7 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
 #endif
     };
     if (DL_DISTPROD || warp == DL_PRODWARP) {
-        for (int step = 0; step < FPREF && step < nsteps; ++step) issue_stage(step);
+        for (int step = 0; step < PREF && step < nsteps; ++step) issue_stage(step);
     }
 
     // ---------------------------------------------------------------------- compute
@@ -252,10 +326,10 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
 
     int it = 0;
     for (int t = t_begin; t < t_end; ++t, ++it) {
-        const int s = it % FSTAGES;
-        const uint32_t ph = (it / FSTAGES) & 1;
-        if ((DL_DISTPROD || warp == DL_PRODWARP) && it + FPREF < nsteps)    // warp-uniform
-            issue_stage(it + FPREF);
+        const int s = it % STG;
+        const uint32_t ph = (it / STG) & 1;
+        if ((DL_DISTPROD || warp == DL_PRODWARP) && it + PREF < nsteps)    // warp-uniform
+            issue_stage(it + PREF);
 #ifdef DL_DBGWAIT
         const long long tw0 = clock64();
         mbar_wait(&full[s], ph);
@@ -304,7 +378,6 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
                 double Eo = E[0];
                 if (!(DL_ASYM && o == FTO - 1 && nto < FTO)) {     // warp-uniform
                 const double* tc = tcw + o * TCS;
-                const double hc = tc[6 * NF + 0], ic = tc[6 * NF + 1];
                 double pOT[ZJ], pTT[ZJ], pOO[ZJ];
 #pragma unroll
                 for (int c = 0; c < ZJ; ++c) {
@@ -315,53 +388,11 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
                         pOT[c] = tc[6 * NF + 2]; pTT[c] = tc[6 * NF + 3]; pOO[c] = tc[6 * NF + 4];
                     }
                 }
-                // pass 0: observed variances only (utils_cy.pyx:101-113 with ellML = 0)
-                double fot[ZJ], ftt[ZJ], foo[ZJ], P[ZJ], e2[ZJ];
-#pragma unroll
-                for (int c = 0; c < ZJ; ++c) { fot[c] = pOT[c]; ftt[c] = pTT[c]; }
-#pragma unroll
-                for (int f = 0; f < NF; ++f) {
-                    const double a = tc[2 * f], w = tc[2 * f + 1];
-#pragma unroll
-                    for (int c = 0; c < ZJ; ++c) {
-                        const double tw = m[c][f] * w;
-                        fot[c] = fma(m[c][f], a, fot[c]);
-                        ftt[c] = fma(tw, m[c][f], ftt[c]);
-                    }
-                }
-#pragma unroll
-                for (int c = 0; c < ZJ; ++c) {
-                    const double ell = fot[c] * rcp_fast(ftt[c]);
-                    e2[c] = ell * (ell * ic);
-                    fot[c] = pOT[c]; ftt[c] = pTT[c]; foo[c] = pOO[c]; P[c] = zev[c];
-                }
-                // pass 1: variance inflated by ell^2 * model variance (utils_cy.pyx:107-112)
-#pragma unroll
-                for (int f = 0; f < NF; ++f) {
-                    const double ov = tc[2 * NF + 4 * f], ob = tc[2 * NF + 4 * f + 1],
-                                 o2 = tc[2 * NF + 4 * f + 2];
-#pragma unroll
-                    for (int c = 0; c < ZJ; ++c) {
-                        const double var = fma(e2[c], cv[c][f], ov);
-                        const double r = rcp_fast(var);
-                        const double tm = m[c][f] * r;
-                        fot[c] = fma(tm, ob, fot[c]);
-                        ftt[c] = fma(tm, m[c][f], ftt[c]);
-                        foo[c] = fma(o2, r, foo[c]);
-                        P[c] *= var;
-                    }
-                }
-                // chi2 and (det)^-1/2 (utils_cy.pyx:111-118)
                 double x[ZJ], y[ZJ], sarg[ZJ];
                 const double R = rvw[2 * o];
+                cells_xy<NF, ZJ>(tc, m, cv, pOT, pTT, pOO, zev, xmask, x, y);
 #pragma unroll
-                for (int c = 0; c < ZJ; ++c) {
-                    y[c] = rsqrt_fast(P[c] * ftt[c]);
-                    const double rF = (y[c] * y[c]) * P[c];      // 1 / FTT
-                    const double chi2 = fma(-(fot[c] * rF), fot[c], foo[c]);
-                    x[c] = fma(hc, chi2, xmask[c]);              // -chi2/2 in the target's units
-                    sarg[c] = x[c] - R;
-                }
+                for (int c = 0; c < ZJ; ++c) sarg[c] = x[c] - R;
 #ifdef DL_DBGWAIT
                 {
                     bool dead = true;
@@ -370,44 +401,44 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
                     dbg_div += __all_sync(0xffffffffu, dead);
                 }
 #endif
+                // Speculate that neither the reference exponent R nor the running max V moves
+                // (they do O(log) times per target): evaluate exp first, then ONE vote covers
+                // both conditions, so the tail of the cell has a single warp-wide
+                // serialisation point.
+                double v[ZJ];
+#pragma unroll
+                for (int c = 0; c < ZJ; ++c) v[c] = exp_nonpos(sarg[c]) * y[c];   // :118,128
+                const double V = rvw[2 * o + 1];
                 bool up = false;
 #pragma unroll
-                for (int c = 0; c < ZJ; ++c) up |= __double2hiint(sarg[c]) > 0;
+                for (int c = 0; c < ZJ; ++c)
+                    up |= (__double2hiint(sarg[c]) > 0) |
+                          (__double_as_longlong(v[c]) > __double_as_longlong(V));
                 if (__any_sync(0xffffffffu, up)) {
-                    // rare: the warp met a better cell than its reference exponent
                     double xl = x[0];
 #pragma unroll
                     for (int c = 1; c < ZJ; ++c) xl = fmax(xl, x[c]);
                     const double xm = warp_max(xl);
+                    double Vc = V;
                     if (xm > R) {
+                        // the warp met a better cell than its reference exponent: rescale
                         const double fs = exp(R - xm);
                         Eo *= fs;
+                        Vc *= fs;
 #pragma unroll
                         for (int zj = 0; zj < FZT; ++zj) pdfw[o * FZC + zj * 32 + lane] *= fs;
                         __syncwarp();
-                        if (lane == 0) { rvw[2 * o] = xm; rvw[2 * o + 1] *= fs; }
+                        if (lane == 0) { rvw[2 * o] = xm; rvw[2 * o + 1] = Vc; }
                         __syncwarp();
 #pragma unroll
-                        for (int c = 0; c < ZJ; ++c) sarg[c] = x[c] - xm;
+                        for (int c = 0; c < ZJ; ++c) v[c] = exp_nonpos(x[c] - xm) * y[c];
                     }
-                }
-                double v[ZJ];
-#pragma unroll
-                for (int c = 0; c < ZJ; ++c) v[c] = exp_nonpos(sarg[c]) * y[c];   // :118,128
-                // running max of the un-priored value (operands >= 0: compare bit patterns on
-                // the integer pipe)
-                const double V = rvw[2 * o + 1];
-                up = false;
-#pragma unroll
-                for (int c = 0; c < ZJ; ++c)
-                    up |= __double_as_longlong(v[c]) > __double_as_longlong(V);
-                if (__any_sync(0xffffffffu, up)) {
                     double vl = v[0];
 #pragma unroll
                     for (int c = 1; c < ZJ; ++c) vl = fmax(vl, v[c]);
                     const double vm = warp_max(vl);
                     __syncwarp();
-                    if (lane == 0) rvw[2 * o + 1] = fmax(V, vm);
+                    if (lane == 0 && vm > Vc) rvw[2 * o + 1] = vm;
                     __syncwarp();
                 }
                 // prior, PDF and evidence accumulation  (delight-apply.py:145-148)
@@ -454,10 +485,11 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
             double* dst = p.pdf_part + ((size_t)split * p.nO + og) * p.nzp + z0;
 #pragma unroll
             for (int zj = 0; zj < FZT; ++zj) dst[zj * 32 + lane] = pdfw[o * FZC + zj * 32 + lane];
+            const double vfin = rvw[2 * o + 1];
             if (lane == 0) {
                 const size_t k = ((size_t)split * p.nchunk + chunk) * p.nO + og;
                 p.Rw[k] = rvw[2 * o];
-                p.Vw[k] = rvw[2 * o + 1];
+                p.Vw[k] = vfin;
             }
         }
     }
@@ -899,8 +931,7 @@ static int launch_fused_t(const FusedParams& p, cudaStream_t stream) {
     constexpr int ZJ = NF <= 8 ? ZJ_SMALL : ZJ_LARGE;
     constexpr int ROWS = 2 * NF + 1;
     constexpr int TCS = tc_stride(NF);
-    const size_t smem = sizeof(double) * (FSTAGES * ROWS * FZC + FTPC * FZC + FTPC * TCS + FTPC * 2 + FZC +
-                                          (ZDEP ? 4 * FZC : 0)) + 2 * FSTAGES * sizeof(uint64_t);
+    const size_t smem = fused_smem_bytes(NF, ZDEP, fused_stages(NF, ZDEP));
     auto kern = fused_like_kernel<NF, ZDEP, ZJ>;
     DL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));

@@ -273,6 +273,11 @@ def test_fused_templatefit_golden(golden, sdss):
     (3, 33, 50, 4, 1, True, None),
     (20, 60, 200, 16, 16, False, None),      # > 8 bands: single-redshift variant of the kernel
     (9, 30, 129, 12, 11, True, 2),
+    # ring depth 3 / 2 / 2 (two CTAs per SM) and 4 (one CTA per SM): fused_stages()
+    (12, 50, 200, 8, 8, True, None),
+    (10, 45, 140, 10, 10, False, None),
+    (8, 40, 129, 13, 13, True, 1),
+    (6, 35, 100, 14, 14, False, None),
 ])
 def test_fused_vs_oracle_random(orc, nO, nT, nz, nB, nf, zdep, nsplit):
     from delight_b200 import apply
