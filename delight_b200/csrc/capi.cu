@@ -244,12 +244,15 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double seed, 
     if (s == 123.456) out[0] = s;     // never true; keeps the chains alive
 }
 __global__ void selftest_math_kernel(long long n, const double* x, double* out) {
+    __shared__ double etab[dl::EXP_TAB];
+    dl::exp_tab_init(etab, threadIdx.x);
+    __syncthreads();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double v = x[i];
     out[i] = dl::rcp_fast(v);
     out[n + i] = dl::rsqrt_fast(v);
-    out[2 * n + i] = dl::exp_nonpos(-v);
+    out[2 * n + i] = dl::exp_nonpos_tab(-v, etab);
     double s0, s1;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(s0) : "d"(v));
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(s1) : "d"(v));
@@ -263,7 +266,7 @@ extern "C" {
 long long dl_launch_count(void) { return g_launches.load(); }
 
 // accuracy self-test of the fast FP64 helpers used by the fused kernel (device pointers):
-// out[0][i] = rcp_fast(x[i]), out[1][i] = rsqrt_fast(x[i]), out[2][i] = exp_nonpos(-x[i]),
+// out[0][i] = rcp_fast(x[i]), out[1][i] = rsqrt_fast(x[i]), out[2][i] = exp_nonpos_tab(-x[i]),
 // out[3][i] = raw MUFU reciprocal seed, out[4][i] = raw MUFU rsqrt seed
 int dl_selftest_math_dev(long long n, const double* x, double* out, void* stream) {
     DL_REQUIRE(n > 0 && x && out, "bad arguments");

@@ -90,6 +90,16 @@ constexpr int FPREF = DL_PREF;      // prefetch distance in steps (< FSTAGES)
 #ifndef DL_ELECT
 #define DL_ELECT 1
 #endif
+// exp through a 32-entry table of 2^(j/32) in shared memory + degree-4 polynomial (8 FP64-pipe
+// instructions) instead of the degree-9 polynomial (14): 1.311 -> 1.279 s at config 3
+#ifndef DL_EXPTAB
+#define DL_EXPTAB 1
+#endif
+#if DL_EXPTAB
+#define DL_EXP(x) exp_nonpos_tab((x), etab)
+#else
+#define DL_EXP(x) exp_nonpos(x)
+#endif
 
 
 constexpr int FTPC = FW * FTO - DL_ASYM;    // targets per CTA
@@ -104,7 +114,8 @@ __host__ __device__ constexpr int tc_stride(int nf) { return 6 * nf + 6; }
 // (228 KB per SM, 1 KB reserved per CTA); beyond 13 bands only one CTA fits anyway.
 __host__ __device__ constexpr size_t fused_smem_bytes(int nf, bool zdep, int stages) {
     return sizeof(double) * ((size_t)stages * (2 * nf + 1) * FZC + FTPC * FZC + FTPC * tc_stride(nf) +
-                             FTPC * 2 + FZC + (zdep ? 4 * FZC : 0)) + 2 * stages * sizeof(uint64_t);
+                             FTPC * 2 + FZC + (zdep ? 4 * FZC : 0) + EXP_TAB) +
+           2 * stages * sizeof(uint64_t);
 }
 __host__ __device__ constexpr int fused_stages(int nf, bool zdep) {
     int s = FSTAGES;
@@ -199,6 +210,7 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
     double* zd_sm = wz_sm + FZC;                                // [4][FZC] (ZDEP only)
     uint64_t* full = reinterpret_cast<uint64_t*>(zd_sm + (ZDEP ? 4 * FZC : 0));
     uint64_t* empty = full + STG;
+    const double* etab = reinterpret_cast<const double*>(empty + STG);   // [EXP_TAB] 2^(j/32)
 
     // Target tile fastest, z-chunk slowest: the ~300 CTAs resident at any time then work on at
     // most two z-chunks, i.e. they stream the SAME 13-row x 128-redshift slices of the model
@@ -227,6 +239,7 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
         o = o < p.nO ? o : p.nO - 1;
         tc_sm[i] = p.tconst[(size_t)o * TCS + (i % TCS)];
     }
+    exp_tab_init(const_cast<double*>(etab), threadIdx.x);
     for (int i = threadIdx.x; i < FTPC * FZC; i += FTHREADS) pdf_sm[i] = 0.0;
     for (int i = threadIdx.x; i < FTPC; i += FTHREADS) { rv_sm[2 * i] = -1e300; rv_sm[2 * i + 1] = 0.0; }
     for (int i = threadIdx.x; i < FZC; i += FTHREADS) {
@@ -407,7 +420,7 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
                 // serialisation point.
                 double v[ZJ];
 #pragma unroll
-                for (int c = 0; c < ZJ; ++c) v[c] = exp_nonpos(sarg[c]) * y[c];   // :118,128
+                for (int c = 0; c < ZJ; ++c) v[c] = DL_EXP(sarg[c]) * y[c];   // :118,128
                 const double V = rvw[2 * o + 1];
                 bool up = false;
 #pragma unroll
@@ -431,7 +444,7 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
                         if (lane == 0) { rvw[2 * o] = xm; rvw[2 * o + 1] = Vc; }
                         __syncwarp();
 #pragma unroll
-                        for (int c = 0; c < ZJ; ++c) v[c] = exp_nonpos(x[c] - xm) * y[c];
+                        for (int c = 0; c < ZJ; ++c) v[c] = DL_EXP(x[c] - xm) * y[c];
                     }
                     double vl = v[0];
 #pragma unroll
