@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double seed, 
 }
 __global__ void selftest_math_kernel(long long n, const double* x, double* out) {
     __shared__ double etab[dl::EXP_TAB];
-    dl::exp_tab_init(etab, threadIdx.x);
+    dl::exp_tab_init(etab, threadIdx.x, blockDim.x);
     __syncthreads();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -95,28 +95,36 @@ __device__ __forceinline__ double exp_nonpos(double x) {
     return (x >= -708.0) ? res : ((__double2hiint(x) & 0x7fffffff) > 0x7ff00000 ? x : 0.0);
 }
 
-// Table variant of the same function: x = (32 k + j) ln2/32 + r, |r| <= ln2/64, so a degree-4
-// polynomial is enough (truncation r^5/120 <= 1.3e-12 relative) and exp(x) = 2^k * tab[j] * p(r)
-// with tab[j] = 2^(j/32) (32 doubles in shared memory, at most a 2-way bank conflict).  8 FP64-pipe
-// instructions instead of 14; the range / NaN tests run on the integer pipe.
-constexpr int EXP_TAB = 32;
-__device__ __forceinline__ void exp_tab_init(double* tab, int tid) {
-    if (tid < EXP_TAB) tab[tid] = exp2((double)tid / EXP_TAB);
+// Table variant of the same function: x = (N k + j) ln2/N + r, |r| <= ln2/(2N), so a short
+// polynomial is enough and exp(x) = 2^k * tab[j] * p(r) with tab[j] = 2^(j/N) in shared memory.
+//   N = 32:  degree 4 (truncation r^5/120 <= 1.3e-12 relative), 8 FP64-pipe instructions
+//   N = 128: degree 3 (truncation r^4/24  <= 2.3e-12 relative), 7 FP64-pipe instructions
+// instead of 14; the range / NaN tests run on the integer pipe.
+#ifndef DL_EXPTAB_BITS
+#define DL_EXPTAB_BITS 7
+#endif
+constexpr int EXP_TAB = 1 << DL_EXPTAB_BITS;
+__device__ __forceinline__ void exp_tab_init(double* tab, int tid, int nthreads) {
+    for (int j = tid; j < EXP_TAB; j += nthreads) tab[j] = exp2((double)j / EXP_TAB);
 }
 __device__ __forceinline__ double exp_nonpos_tab(double x, const double* tab) {
-    const double L2E32 = 46.166241308446828384;        // 32 / ln 2
-    const double LN2_32 = 2.1660849392498290195e-02;   // ln 2 / 32
-    const double SHIFT = 6755399441055744.0;           // 1.5 * 2^52
-    const double t = fma(x, L2E32, SHIFT);
+    const double L2EN = 1.4426950408889634074 * EXP_TAB;           // N / ln 2
+    const double LN2N = 6.93147180559945286227e-01 / EXP_TAB;      // ln 2 / N (exact scaling)
+    const double SHIFT = 6755399441055744.0;                       // 1.5 * 2^52
+    const double t = fma(x, L2EN, SHIFT);
     const int n = __double2loint(t);
     const double fn = t - SHIFT;
-    const double r = fma(-fn, LN2_32, x);
+    const double r = fma(-fn, LN2N, x);
+#if DL_EXPTAB_BITS >= 7
+    double p = fma(r, 1.66666666666666666667e-01, 0.5);
+#else
     double p = fma(r, 4.16666666666666666667e-02, 1.66666666666666666667e-01);
     p = fma(p, r, 0.5);
+#endif
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
     p *= tab[n & (EXP_TAB - 1)];
-    const int hi = __double2hiint(p) + ((n >> 5) << 20);
+    const int hi = __double2hiint(p) + ((n >> DL_EXPTAB_BITS) << 20);
     const double res = __hiloint2double(hi, __double2loint(p));
     // x < -708 (incl. -inf) -> 0, NaN -> NaN; both decided on the high word
     const unsigned hx = (unsigned)__double2hiint(x);

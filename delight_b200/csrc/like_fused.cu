@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
         o = o < p.nO ? o : p.nO - 1;
         tc_sm[i] = p.tconst[(size_t)o * TCS + (i % TCS)];
     }
-    exp_tab_init(const_cast<double*>(etab), threadIdx.x);
+    exp_tab_init(const_cast<double*>(etab), threadIdx.x, FTHREADS);
     for (int i = threadIdx.x; i < FTPC * FZC; i += FTHREADS) pdf_sm[i] = 0.0;
     for (int i = threadIdx.x; i < FTPC; i += FTHREADS) { rv_sm[2 * i] = -1e300; rv_sm[2 * i + 1] = 0.0; }
     for (int i = threadIdx.x; i < FZC; i += FTHREADS) {
