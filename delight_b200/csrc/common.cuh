@@ -99,6 +99,7 @@ __device__ __forceinline__ double exp_nonpos(double x) {
 // polynomial is enough and exp(x) = 2^k * tab[j] * p(r) with tab[j] = 2^(j/N) in shared memory.
 //   N = 32:  degree 4 (truncation r^5/120 <= 1.3e-12 relative), 8 FP64-pipe instructions
 //   N = 128: degree 3 (truncation r^4/24  <= 2.3e-12 relative), 7 FP64-pipe instructions
+// (N = 1024 with degree 2 measured no faster: 1.268 s.)
 // instead of 14; the range / NaN tests run on the integer pipe.
 #ifndef DL_EXPTAB_BITS
 #define DL_EXPTAB_BITS 7

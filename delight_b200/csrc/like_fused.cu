@@ -106,7 +106,8 @@ constexpr int FTPC = FW * FTO - DL_ASYM;    // targets per CTA
 constexpr int FTHREADS = FW * 32;
 constexpr int MAXNF = 16;
 
-// per-target constants: [f][2] = (a', w') | [f][4] = (var', obs, obs^2, 0) | hc ic pOT pTT pOO c
+// per-target constants: [f][2] = (a' s, w') | [f][4] = (var', obs, obs^2, 0 (f = 0: c s)) |
+// hc, pOT s, pOT, pTT, pOO, c   with s = sqrt(cov_scale / c)
 __host__ __device__ constexpr int tc_stride(int nf) { return 6 * nf + 6; }
 
 // Shared memory of one CTA with a ring of `stages`, and the ring depth used for NF bands: the
@@ -144,15 +145,16 @@ struct FusedParams {
 // tc: the target's constants, m / cv: band means / variances of the cells.
 template <int NF, int ZJ>
 __device__ __forceinline__ void cells_xy(const double* tc, const double (&m)[ZJ][NF],
-                                         const double (&cv)[ZJ][NF], const double (&pOT)[ZJ],
+                                         const double (&cv)[ZJ][NF], const double (&pOT0)[ZJ],
+                                         const double (&pOT)[ZJ],
                                          const double (&pTT)[ZJ], const double (&pOO)[ZJ],
                                          const double (&zev)[ZJ], const double (&xmask)[ZJ],
                                          double (&x)[ZJ], double (&y)[ZJ]) {
-    const double hc = tc[6 * NF + 0], ic = tc[6 * NF + 1];
+    const double hc = tc[6 * NF + 0];
     // pass 0: observed variances only (utils_cy.pyx:101-113 with ellML = 0)
     double fot[ZJ], ftt[ZJ], foo[ZJ], P[ZJ], e2[ZJ];
 #pragma unroll
-    for (int c = 0; c < ZJ; ++c) { fot[c] = pOT[c]; ftt[c] = pTT[c]; }
+    for (int c = 0; c < ZJ; ++c) { fot[c] = pOT0[c]; ftt[c] = pTT[c]; }
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
         const double a = tc[2 * f], w = tc[2 * f + 1];
@@ -165,8 +167,8 @@ __device__ __forceinline__ void cells_xy(const double* tc, const double (&m)[ZJ]
     }
 #pragma unroll
     for (int c = 0; c < ZJ; ++c) {
-        const double ell = fot[c] * rcp_fast(ftt[c]);
-        e2[c] = ell * (ell * ic);
+        const double ell = fot[c] * rcp_fast(ftt[c]);     // ellML * sqrt(cov_scale / c)
+        e2[c] = ell * ell;
         fot[c] = pOT[c]; ftt[c] = pTT[c]; foo[c] = pOO[c]; P[c] = zev[c];
     }
     // pass 1: variance inflated by ell^2 * model variance (utils_cy.pyx:107-112)
@@ -391,19 +393,21 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
                 double Eo = E[0];
                 if (!(DL_ASYM && o == FTO - 1 && nto < FTO)) {     // warp-uniform
                 const double* tc = tcw + o * TCS;
-                double pOT[ZJ], pTT[ZJ], pOO[ZJ];
+                double pOT0[ZJ], pOT[ZJ], pTT[ZJ], pOO[ZJ];
 #pragma unroll
                 for (int c = 0; c < ZJ; ++c) {
                     if (ZDEP) {
                         const double cc = tc[6 * NF + 5];
+                        pOT0[c] = tc[2 * NF + 3] * zot[c];
                         pOT[c] = cc * zot[c]; pTT[c] = cc * ztt[c]; pOO[c] = cc * zoo[c];
                     } else {
+                        pOT0[c] = tc[6 * NF + 1];
                         pOT[c] = tc[6 * NF + 2]; pTT[c] = tc[6 * NF + 3]; pOO[c] = tc[6 * NF + 4];
                     }
                 }
                 double x[ZJ], y[ZJ], sarg[ZJ];
                 const double R = rvw[2 * o];
-                cells_xy<NF, ZJ>(tc, m, cv, pOT, pTT, pOO, zev, xmask, x, y);
+                cells_xy<NF, ZJ>(tc, m, cv, pOT0, pOT, pTT, pOO, zev, xmask, x, y);
 #pragma unroll
                 for (int c = 0; c < ZJ; ++c) sarg[c] = x[c] - R;
 #ifdef DL_DBGWAIT
@@ -525,11 +529,12 @@ __global__ void prep_targets_kernel(int nO, int NF, const double* __restrict__ o
     int k = (int)rint(s / NF);
     k = k < -1000 ? -1000 : (k > 1000 ? 1000 : k);
     const double c = ldexp(1.0, k), ic = ldexp(1.0, -k);
+    const double sic = sqrt(ic * cov_scale);   // ell^2 * (cov_scale * model variance) / c
     for (int f = 0; f < NF; ++f) {
         const double ob = obs[(size_t)o * NF + f];
         const double vs = var[(size_t)o * NF + f] * ic;
         const double w = 1.0 / vs;
-        tc[2 * f] = ob * w;
+        tc[2 * f] = ob * w * sic;       // pass-0 weights carry sqrt(ic cov_scale): e2 = (FOT'/FTT)^2
         tc[2 * f + 1] = w;
         tc[2 * NF + 4 * f] = vs;
         tc[2 * NF + 4 * f + 1] = ob;
@@ -537,7 +542,8 @@ __global__ void prep_targets_kernel(int nO, int NF, const double* __restrict__ o
         tc[2 * NF + 4 * f + 3] = 0.0;
     }
     tc[6 * NF + 0] = -0.5 * ic;
-    tc[6 * NF + 1] = ic * cov_scale;   // ell^2 * (cov_scale * model variance) / c
+    tc[6 * NF + 1] = c * (ell_hat / ell_var) * sic;   // pass-0 start value of FOT'
+    tc[2 * NF + 3] = c * sic;                          // same for z-dependent ell priors
     tc[6 * NF + 2] = c * (ell_hat / ell_var);
     tc[6 * NF + 3] = c / ell_var;
     tc[6 * NF + 4] = c * (ell_hat * ell_hat / ell_var);
