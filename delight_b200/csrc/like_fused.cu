@@ -535,6 +535,27 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
             }
         }
         // evidence of (target, training galaxy t) over this z-chunk
+#if DL_FTO == 4 && !DL_ASYM
+        {
+            // four warp sums folded into one butterfly: after the xor-16 step a lane keeps two of
+            // the four partial sums, after xor-8 one; lane 8 k ends up with the sum of target k
+            // (6 shuffle + add steps instead of 20)
+            const bool hi16 = lane & 16, hi8 = lane & 8;
+            const double s0 = hi16 ? E[0] : E[2], s1 = hi16 ? E[1] : E[3];      // what I give away
+            double k0 = hi16 ? E[2] : E[0], k1 = hi16 ? E[3] : E[1];            // what I keep
+            k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+            k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+            double ev = (hi8 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, hi8 ? k0 : k1, 8);
+            ev += __shfl_xor_sync(0xffffffffu, ev, 4);
+            ev += __shfl_xor_sync(0xffffffffu, ev, 2);
+            ev += __shfl_xor_sync(0xffffffffu, ev, 1);
+            const int o = lane >> 3;                   // (bit 4, bit 3) = (target >> 1, target & 1)
+            const int og = og0 + o;
+            if ((lane & 7) == 0 && og < p.nO)
+                p.evid_part[((size_t)chunk * p.nO + og) * p.nT + t] =
+                    make_double2(ev, rvw[2 * o]);
+        }
+#else
 #pragma unroll
         for (int o = 0; o < FTO; ++o) E[o] = warp_sum(E[o]);
         {
@@ -546,6 +567,7 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
                 p.evid_part[((size_t)chunk * p.nO + og) * p.nT + t] =
                     make_double2(ev, rvw[2 * lane]);
         }
+#endif
 #pragma unroll
         for (int o = 0; o < FTO; ++o) E[o] = 0.0;
         __syncwarp();
