@@ -7,7 +7,7 @@
 // target never exists in HBM.
 //
 // Work decomposition (B200: 148 SMs, FP64 pipe = 16 lanes / SMSP, 227 KB smem / SM)
-//   CTA      = 8 warps (lane 0 of warp 0 also drives TMA); 2 CTAs / SM (96 KB smem, <=128 regs)
+//   CTA      = 8 warps (warp 0 also drives TMA); 2 CTAs / SM (97 KB smem, <=128 regs)
 //   CTA tile = one z-chunk of 128 redshifts  x  32 targets (4 per compute warp)
 //              x  a contiguous range of training galaxies (all of them unless nsplit > 1)
 //   lane     = 4 redshifts of the chunk (z = z0 + 32*j + lane) -> conflict-free smem rows
@@ -15,10 +15,11 @@
 //              variances, the prior row) of 128 doubles each, fetched with 1-D TMA bulk copies
 //              (cp.async.bulk ... mbarrier::complete_tx) into a full/empty mbarrier ring
 //   compute  = per (target, training galaxy, z) cell, all in FP64 on the vector pipe:
-//              pass 0 with the observed variances only (2 FMA / band, per-target constants
-//              broadcast from smem), one reciprocal for the luminosity scale, pass 1 with the
-//              model variance folded in (1 reciprocal + 6 FMA-class ops / band), then
-//              chi2, (prod var * FTT)^-1/2 by one rsqrt, one exp.  No log, no division.
+//              pass 0 with the observed variances only (3 FMA-class ops / band, per-target
+//              constants broadcast from smem), one reciprocal for the luminosity scale, pass 1
+//              with the model variance folded in (one reciprocal per PAIR of bands + 7 FMA-class
+//              ops / band), then chi2, (prod var * FTT)^-1/2 by one rsqrt, one table-based exp.
+//              No log, no division; 96 FP64-pipe instructions per cell at 6 bands.
 //
 // Normalisation.  The reference subtracts the GLOBAL max log-likelihood of a target before
 // exp (utils_cy.pyx:120-128).  Here every warp keeps, per target, a lazily updated reference
@@ -90,8 +91,9 @@ constexpr int FPREF = DL_PREF;      // prefetch distance in steps (< FSTAGES)
 #ifndef DL_ELECT
 #define DL_ELECT 1
 #endif
-// exp through a 32-entry table of 2^(j/32) in shared memory + degree-4 polynomial (8 FP64-pipe
-// instructions) instead of the degree-9 polynomial (14): 1.311 -> 1.279 s at config 3
+// exp through a table of 2^(j/128) in shared memory + degree-3 polynomial (7 FP64-pipe
+// instructions) instead of the degree-9 polynomial (14): 1.311 -> 1.267 s at config 3.
+// DL_PAIRRCP = 2 / 3: one reciprocal per pair / triple of bands in pass 1 (0: one per band).
 #ifndef DL_EXPTAB
 #define DL_EXPTAB 1
 #endif
