@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _lib
 
-FUSED_MAX_BANDS = 16
+FUSED_MAX_BANDS = 32
 
 
 def partition(n, rank, size):

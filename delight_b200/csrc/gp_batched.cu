@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(PRED_THREADS) gp_predict_kernel(
     // coarse -> fine grid, linear (photoz_gp.py:321-335), into the fused layout
     for (int i = tid; i < nB * nzp; i += PRED_THREADS) {
         const int b = i / nzp, zf = i % nzp;
-        double mval = 0.0, vval = 1.0;
+        double mval = 0.0, vval = 0.0;       // padding: mean 0, model variance 0
         if (zf < nz) {
             const double zv = gm.zgrid[zf];
             const int lo = bin_left(gm.zGP, nzg, zv);

@@ -79,9 +79,6 @@ constexpr int FPREF = DL_PREF;      // prefetch distance in steps (< FSTAGES)
 #ifndef DL_ASYM
 #define DL_ASYM 0
 #endif
-#ifndef DL_ROLL_O
-#define DL_ROLL_O 0
-#endif
 #ifndef DL_DISTPROD
 #define DL_DISTPROD 0
 #endif
@@ -109,7 +106,8 @@ constexpr int FPREF = DL_PREF;      // prefetch distance in steps (< FSTAGES)
 
 constexpr int FTPC = FW * FTO - DL_ASYM;    // targets per CTA
 constexpr int FTHREADS = FW * 32;
-constexpr int MAXNF = 16;
+constexpr int MAXNF = 32;   // bands per target group
+constexpr int REGNF = 16;   // up to here the model values of a z-group are cached in registers
 
 // per-target constants: [f][2] = (a' s, w') | [f][4] = (var', obs, obs^2, 0 (f = 0: c s)) |
 // hc, pOT s, pOT, pTT, pOO, c   with s = sqrt(cov_scale / c)
@@ -126,7 +124,10 @@ __host__ __device__ constexpr size_t fused_smem_bytes(int nf, bool zdep, int sta
 __host__ __device__ constexpr int fused_stages(int nf, bool zdep) {
     int s = FSTAGES;
     while (s > 2 && 2 * (fused_smem_bytes(nf, zdep, s) + 1024) > 228 * 1024) --s;
-    if (2 * (fused_smem_bytes(nf, zdep, s) + 1024) > 228 * 1024) s = FSTAGES;   // one CTA per SM
+    if (2 * (fused_smem_bytes(nf, zdep, s) + 1024) > 228 * 1024) {
+        s = FSTAGES;                                                            // one CTA per SM
+        while (s > 2 && fused_smem_bytes(nf, zdep, s) > 227 * 1024) --s;
+    }
     return s;
 }
 
@@ -148,16 +149,32 @@ struct FusedParams {
 // x = -chi2/2 (in the target's units, + the padding mask) and y = (det)^-1/2 of ZJ cells of one
 // target against one training galaxy: utils_cy.pyx:98-118 restructured (see the header comment).
 // tc: the target's constants, m / cv: band means / variances of the cells.
+// Where the band means / variances of the ZJ cells come from: registers (loaded once per z-group
+// and reused by the warp's targets; NF <= 16) or the stage in shared memory (NF > 16: 2 NF ZJ
+// doubles do not fit the register budget, every use is an LDS).
 template <int NF, int ZJ>
-__device__ __forceinline__ void cells_xy(const double* tc, const double (&m)[ZJ][NF],
-                                         const double (&cv)[ZJ][NF], const double (&pOT0)[ZJ],
+struct RegModel {
+    const double (&mm)[ZJ][NF];
+    const double (&cc)[ZJ][NF];
+    __device__ __forceinline__ double m(int c, int f) const { return mm[c][f]; }
+    __device__ __forceinline__ double cv(int c, int f) const { return cc[c][f]; }
+};
+template <int NF, int ZJ>
+struct SmemModel {
+    const double* stz;      // stage + the lane's first redshift
+    __device__ __forceinline__ double m(int c, int f) const { return stz[f * FZC + 32 * c]; }
+    __device__ __forceinline__ double cv(int c, int f) const { return stz[(NF + f) * FZC + 32 * c]; }
+};
+
+template <int NF, int ZJ, class Model>
+__device__ __forceinline__ void cells_xy(const double* tc, const Model md, const double (&pOT0)[ZJ],
                                          const double (&pOT)[ZJ],
                                          const double (&pTT)[ZJ], const double (&pOO)[ZJ],
                                          const double (&zev)[ZJ], const double (&xmask)[ZJ],
                                          double (&x)[ZJ], double (&y)[ZJ]) {
     const double hc = tc[6 * NF + 0];
     // pass 0: observed variances only (utils_cy.pyx:101-113 with ellML = 0)
-    double fot[ZJ], ftt[ZJ], foo[ZJ], P[ZJ], e2[ZJ];
+    double fot[ZJ], ftt[ZJ], foo[ZJ], P[ZJ], P2[ZJ], e2[ZJ];   // det = P * P2 (P2 only for NF > REGNF)
 #pragma unroll
     for (int c = 0; c < ZJ; ++c) { fot[c] = pOT0[c]; ftt[c] = pTT[c]; }
 #pragma unroll
@@ -165,16 +182,17 @@ __device__ __forceinline__ void cells_xy(const double* tc, const double (&m)[ZJ]
         const double a = tc[2 * f], w = tc[2 * f + 1];
 #pragma unroll
         for (int c = 0; c < ZJ; ++c) {
-            const double tw = m[c][f] * w;
-            fot[c] = fma(m[c][f], a, fot[c]);
-            ftt[c] = fma(tw, m[c][f], ftt[c]);
+            const double mf = md.m(c, f);
+            const double tw = mf * w;
+            fot[c] = fma(mf, a, fot[c]);
+            ftt[c] = fma(tw, mf, ftt[c]);
         }
     }
 #pragma unroll
     for (int c = 0; c < ZJ; ++c) {
         const double ell = fot[c] * rcp_fast(ftt[c]);     // ellML * sqrt(cov_scale / c)
         e2[c] = ell * ell;
-        fot[c] = pOT[c]; ftt[c] = pTT[c]; foo[c] = pOO[c]; P[c] = zev[c];
+        fot[c] = pOT[c]; ftt[c] = pTT[c]; foo[c] = pOO[c]; P[c] = zev[c]; P2[c] = 1.0;
     }
     // pass 1: variance inflated by ell^2 * model variance (utils_cy.pyx:107-112)
 #if DL_PAIRRCP >= 2
@@ -183,9 +201,10 @@ __device__ __forceinline__ void cells_xy(const double* tc, const double (&m)[ZJ]
     // the determinant.  Pairs: 9 FP64 instructions + 1 MUFU instead of 10 + 2; triples: 13 + 1
     // instead of 15 + 3.
     auto acc = [&](int c, int f, double r) {
-        const double tm = m[c][f] * r;
+        const double mf = md.m(c, f);
+        const double tm = mf * r;
         fot[c] = fma(tm, tc[2 * NF + 4 * f + 1], fot[c]);
-        ftt[c] = fma(tm, m[c][f], ftt[c]);
+        ftt[c] = fma(tm, mf, ftt[c]);
         foo[c] = fma(tc[2 * NF + 4 * f + 2], r, foo[c]);
     };
     constexpr int G = DL_PAIRRCP;
@@ -194,23 +213,23 @@ __device__ __forceinline__ void cells_xy(const double* tc, const double (&m)[ZJ]
     for (int f = 0; f < NG; f += G) {
 #pragma unroll
         for (int c = 0; c < ZJ; ++c) {
-            const double va = fma(e2[c], cv[c][f], tc[2 * NF + 4 * f]);
-            const double vb = fma(e2[c], cv[c][f + 1], tc[2 * NF + 4 * (f + 1)]);
+            const double va = fma(e2[c], md.cv(c, f), tc[2 * NF + 4 * f]);
+            const double vb = fma(e2[c], md.cv(c, f + 1), tc[2 * NF + 4 * (f + 1)]);
             const double pab = va * vb;
             if (G == 2) {
                 const double ri = rcp_fast(pab);
                 acc(c, f, vb * ri);
                 acc(c, f + 1, va * ri);
-                P[c] *= pab;
+                if (NF > REGNF && f >= NF / 2) P2[c] *= pab; else P[c] *= pab;
             } else {
-                const double vc = fma(e2[c], cv[c][f + 2], tc[2 * NF + 4 * (f + 2)]);
+                const double vc = fma(e2[c], md.cv(c, f + 2), tc[2 * NF + 4 * (f + 2)]);
                 const double pabc = pab * vc;
                 const double ri = rcp_fast(pabc);
                 const double rab = ri * vc;       // 1 / (va vb)
                 acc(c, f, vb * rab);
                 acc(c, f + 1, va * rab);
                 acc(c, f + 2, ri * pab);
-                P[c] *= pabc;
+                if (NF > REGNF && f >= NF / 2) P2[c] *= pabc; else P[c] *= pabc;
             }
         }
     }
@@ -218,21 +237,21 @@ __device__ __forceinline__ void cells_xy(const double* tc, const double (&m)[ZJ]
         constexpr int f = NG < NF - 1 ? NG : 0;
 #pragma unroll
         for (int c = 0; c < ZJ; ++c) {
-            const double va = fma(e2[c], cv[c][f], tc[2 * NF + 4 * f]);
-            const double vb = fma(e2[c], cv[c][f + 1], tc[2 * NF + 4 * (f + 1)]);
+            const double va = fma(e2[c], md.cv(c, f), tc[2 * NF + 4 * f]);
+            const double vb = fma(e2[c], md.cv(c, f + 1), tc[2 * NF + 4 * (f + 1)]);
             const double pab = va * vb;
             const double ri = rcp_fast(pab);
             acc(c, f, vb * ri);
             acc(c, f + 1, va * ri);
-            P[c] *= pab;
+            if (NF > REGNF) P2[c] *= pab; else P[c] *= pab;
         }
     } else if (NF - NG == 1) {
         constexpr int f = NF - 1;
 #pragma unroll
         for (int c = 0; c < ZJ; ++c) {
-            const double var = fma(e2[c], cv[c][f], tc[2 * NF + 4 * f]);
+            const double var = fma(e2[c], md.cv(c, f), tc[2 * NF + 4 * f]);
             acc(c, f, rcp_fast(var));
-            P[c] *= var;
+            if (NF > REGNF) P2[c] *= var; else P[c] *= var;
         }
     }
 #else
@@ -242,11 +261,12 @@ __device__ __forceinline__ void cells_xy(const double* tc, const double (&m)[ZJ]
                      o2 = tc[2 * NF + 4 * f + 2];
 #pragma unroll
         for (int c = 0; c < ZJ; ++c) {
-            const double var = fma(e2[c], cv[c][f], ov);
+            const double var = fma(e2[c], md.cv(c, f), ov);
             const double r = rcp_fast(var);
-            const double tm = m[c][f] * r;
+            const double mf = md.m(c, f);
+            const double tm = mf * r;
             fot[c] = fma(tm, ob, fot[c]);
-            ftt[c] = fma(tm, m[c][f], ftt[c]);
+            ftt[c] = fma(tm, mf, ftt[c]);
             foo[c] = fma(o2, r, foo[c]);
             P[c] *= var;
         }
@@ -255,8 +275,17 @@ __device__ __forceinline__ void cells_xy(const double* tc, const double (&m)[ZJ]
     // chi2 and (det)^-1/2 (utils_cy.pyx:111-118)
 #pragma unroll
     for (int c = 0; c < ZJ; ++c) {
-        y[c] = rsqrt_fast(P[c] * ftt[c]);
-        const double rF = (y[c] * y[c]) * P[c];      // 1 / FTT
+        double rF;
+        if (NF > REGNF) {
+            // many bands: the determinant is kept as two factors so that it cannot leave the
+            // double range (model variance >> observed variance in every band), and 1/FTT has
+            // its own reciprocal
+            y[c] = rsqrt_fast(P[c] * ftt[c]) * rsqrt_fast(P2[c]);
+            rF = rcp_fast(ftt[c]);
+        } else {
+            y[c] = rsqrt_fast(P[c] * ftt[c]);
+            rF = (y[c] * y[c]) * P[c];               // 1 / FTT
+        }
         const double chi2 = fma(-(fot[c] * rF), fot[c], foo[c]);
         x[c] = fma(hc, chi2, xmask[c]);              // -chi2/2 in the target's units
     }
@@ -418,20 +447,22 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
         mbar_wait(&full[s], ph);
 #endif
         const double* st = stage + s * ROWS * FZC;
-#ifdef DL_NO_GRPUNROLL
-#pragma unroll 1
-#else
-#pragma unroll
-#endif
+        // fully unrolled for the register-cached variants; rolled for NF > REGNF (code size and
+        // compile time: 4 x 4 x NF bands otherwise)
+#pragma unroll (NF > REGNF ? 1 : FZT / ZJ)
         for (int grp = 0; grp < FZT / ZJ; ++grp) {
             const int zl = grp * 32 * ZJ + lane;      // cells: zl + 32 c, c < ZJ
-            double m[ZJ][NF], cv[ZJ][NF];
+            constexpr bool SMODEL = NF > REGNF;           // model values stay in the stage
+            constexpr int RN = SMODEL ? 1 : NF;
+            double m[ZJ][RN], cv[ZJ][RN];
+            if (!SMODEL) {
 #pragma unroll
-            for (int f = 0; f < NF; ++f) {
+                for (int f = 0; f < RN; ++f) {
 #pragma unroll
-                for (int c = 0; c < ZJ; ++c) {
-                    m[c][f] = st[f * FZC + zl + 32 * c];
-                    cv[c][f] = st[(NF + f) * FZC + zl + 32 * c];
+                    for (int c = 0; c < ZJ; ++c) {
+                        m[c][f] = st[f * FZC + zl + 32 * c];
+                        cv[c][f] = st[(NF + f) * FZC + zl + 32 * c];
+                    }
                 }
             }
             double pr[ZJ], wzv[ZJ], xmask[ZJ], zot[ZJ], ztt[ZJ], zoo[ZJ], zev[ZJ];
@@ -447,11 +478,7 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
                     zoo[c] = zd_sm[2 * FZC + zl + 32 * c]; zev[c] = zd_sm[3 * FZC + zl + 32 * c];
                 }
             }
-#if DL_ROLL_O
-#pragma unroll 1
-#else
-#pragma unroll
-#endif
+#pragma unroll (NF > REGNF ? 1 : FTO)
             for (int o = 0; o < FTO; ++o) {
                 // E[] is rotated once per target so the loop can stay rolled with the
                 // accumulators in registers (FTO rotations restore the order)
@@ -472,7 +499,12 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
                 }
                 double x[ZJ], y[ZJ], sarg[ZJ];
                 const double R = rvw[2 * o];
-                cells_xy<NF, ZJ>(tc, m, cv, pOT0, pOT, pTT, pOO, zev, xmask, x, y);
+                if constexpr (SMODEL)
+                    cells_xy<NF, ZJ>(tc, SmemModel<NF, ZJ>{st + zl}, pOT0, pOT, pTT, pOO, zev,
+                                     xmask, x, y);
+                else
+                    cells_xy<NF, ZJ>(tc, RegModel<NF, ZJ>{m, cv}, pOT0, pOT, pTT, pOO, zev, xmask,
+                                     x, y);
 #pragma unroll
                 for (int c = 0; c < ZJ; ++c) sarg[c] = x[c] - R;
 #ifdef DL_DBGWAIT
@@ -996,7 +1028,7 @@ __global__ void relayout_grid_kernel(int nz, int nT, int nB, int nzp,
     for (int i = threadIdx.x; i < 32 * nB; i += blockDim.x) {
         const int zz = i / nB, b = i % nB;
         const int z = zb + zz;
-        double a = 0.0, c = 1.0;
+        double a = 0.0, c = 0.0;            // padding: mean 0, model variance 0
         if (z < nz) {
             a = mean[((size_t)z * nT + t) * nB + b];
             c = covar[((size_t)z * nT + t) * nB + b];
@@ -1035,8 +1067,6 @@ __global__ void relayout_prior_kernel(int nz, int nT, int nzp, const double* __r
 template <int NF, bool ZDEP>
 static int launch_fused_t(const FusedParams& p, cudaStream_t stream) {
     constexpr int ZJ = NF <= 8 ? ZJ_SMALL : ZJ_LARGE;
-    constexpr int ROWS = 2 * NF + 1;
-    constexpr int TCS = tc_stride(NF);
     const size_t smem = fused_smem_bytes(NF, ZDEP, fused_stages(NF, ZDEP));
     auto kern = fused_like_kernel<NF, ZDEP, ZJ>;
     DL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1070,6 +1100,22 @@ static int launch_fused_nf(int NF, const FusedParams& p, cudaStream_t stream) {
         case 14: return launch_fused_t<14, ZDEP>(p, stream);
         case 15: return launch_fused_t<15, ZDEP>(p, stream);
         case 16: return launch_fused_t<16, ZDEP>(p, stream);
+        case 17: return launch_fused_t<17, ZDEP>(p, stream);
+        case 18: return launch_fused_t<18, ZDEP>(p, stream);
+        case 19: return launch_fused_t<19, ZDEP>(p, stream);
+        case 20: return launch_fused_t<20, ZDEP>(p, stream);
+        case 21: return launch_fused_t<21, ZDEP>(p, stream);
+        case 22: return launch_fused_t<22, ZDEP>(p, stream);
+        case 23: return launch_fused_t<23, ZDEP>(p, stream);
+        case 24: return launch_fused_t<24, ZDEP>(p, stream);
+        case 25: return launch_fused_t<25, ZDEP>(p, stream);
+        case 26: return launch_fused_t<26, ZDEP>(p, stream);
+        case 27: return launch_fused_t<27, ZDEP>(p, stream);
+        case 28: return launch_fused_t<28, ZDEP>(p, stream);
+        case 29: return launch_fused_t<29, ZDEP>(p, stream);
+        case 30: return launch_fused_t<30, ZDEP>(p, stream);
+        case 31: return launch_fused_t<31, ZDEP>(p, stream);
+        case 32: return launch_fused_t<32, ZDEP>(p, stream);
     }
     dl_set_error("fused likelihood supports 1..%d bands per target group, got %d", MAXNF, NF);
     return DL_ERR_UNSUPPORTED;
@@ -1160,7 +1206,7 @@ int dl_like_fused_dev(long long nO, long long nT, long long nz, long long nB, in
                       long long workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     DL_REQUIRE(nO > 0 && nT > 0 && nz > 1 && nB > 0, "bad shape");
-    DL_REQUIRE(nf >= 1 && nf <= MAXNF, "1..16 bands per target group");
+    DL_REQUIRE(nf >= 1 && nf <= MAXNF, "1..32 bands per target group");
     DL_REQUIRE(nsplit >= 1 && nsplit <= nT, "bad nsplit");
     DL_REQUIRE(K >= 0 && K <= TK_MAXK && K <= nT, "0 <= K <= min(nT, 1024)");
     DL_REQUIRE(ld_pdf >= nz, "ld_pdf < nz");

@@ -118,7 +118,7 @@ int dl_kernel_grids_dev(long long nB, long long nzg, long long NC, long long NL,
 
 /* Model-grid layout of the fused likelihood: [nT][2*nB][nzp], rows 0..nB-1 = band means,
  * nB..2nB-1 = band variances, z contiguous, nzp = dl_fused_padded_nz(nz) (padding: mean 0,
- * variance 1).  Priors are [nT][nzp] (padding 0). */
+ * variance 0).  Priors are [nT][nzp] (padding 0). */
 int dl_fused_chunk(void);
 int dl_fused_targets_per_cta(void);
 long long dl_fused_padded_nz(long long nz);
@@ -137,7 +137,8 @@ int dl_zprior_dev(long long nT, long long nz, const double* zgrid, const double*
 
 /* Fused likelihood + apply epilogue   replaces scripts/delight-apply.py:137-162 x nO targets
  * (approx_flux_likelihood_cy, like*=prior, pdf=sum_t, evid=trapz_z, top-K) for one group of
- * targets that share the band list `bands` (HOST array, nf <= 16 entries).
+ * targets that share the band list `bands` (HOST array, nf <= 32 entries; up to 16 bands the
+ * model values of a redshift group are cached in registers, beyond that re-read from the stage).
  *   obs/var [nO][nf]; ell_hat/ell_var scalars, or device vectors ell_hat_z/ell_var_z [nz]
  *   pdf [nO][ld_pdf] out; evid [nO][nT] out or NULL; top_idx [nO][K] / top_ev [nO][K] out
  *   (K = 0: skipped).  Ties: descending evidence, equal -> larger index first.
