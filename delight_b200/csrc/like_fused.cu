@@ -107,7 +107,17 @@ constexpr int FPREF = DL_PREF;      // prefetch distance in steps (< FSTAGES)
 constexpr int FTPC = FW * FTO - DL_ASYM;    // targets per CTA
 constexpr int FTHREADS = FW * 32;
 constexpr int MAXNF = 32;   // bands per target group
-constexpr int REGNF = 16;   // up to here the model values of a z-group are cached in registers
+// Band counts above DL_REGNF keep the model values in the stage (shared memory) instead of in
+// registers, which leaves room for redshift PAIRS there too.  Measured (2048 x 1500 x 1500 cells,
+// ms, REGNF 16 / ZJ 1 -> REGNF 8 / ZJ 2): nf 9: 64.7 -> 61.6, 13: 86.6 -> 81.4, 14: 128 -> 100,
+// 16: 136 -> 118, 28: 206 -> 195.
+#ifndef DL_REGNF
+#define DL_REGNF 8
+#endif
+#ifndef DL_SMODEL_ZJ
+#define DL_SMODEL_ZJ 2
+#endif
+constexpr int REGNF = DL_REGNF;   // up to here the model values of a z-group are cached in registers
 
 // per-target constants: [f][2] = (a' s, w') | [f][4] = (var', obs, obs^2, 0 (f = 0: c s)) |
 // hc, pOT s, pOT, pTT, pOO, c   with s = sqrt(cov_scale / c)
@@ -1066,7 +1076,7 @@ __global__ void relayout_prior_kernel(int nz, int nT, int nzp, const double* __r
 
 template <int NF, bool ZDEP>
 static int launch_fused_t(const FusedParams& p, cudaStream_t stream) {
-    constexpr int ZJ = NF <= 8 ? ZJ_SMALL : ZJ_LARGE;
+    constexpr int ZJ = NF > REGNF ? DL_SMODEL_ZJ : (NF <= 8 ? ZJ_SMALL : ZJ_LARGE);
     const size_t smem = fused_smem_bytes(NF, ZDEP, fused_stages(NF, ZDEP));
     auto kern = fused_like_kernel<NF, ZDEP, ZJ>;
     DL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -12,7 +12,7 @@ nO, nT = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (2048, 1
 nz = 1500
 L = _lib.lib()
 zgrid = np.linspace(0.01, 3.0, nz)
-for nf in (4, 6, 8, 10, 13, 16, 21, 28):
+for nf in (9, 10, 12, 13, 14, 16, 21, 28):
     g = torch.Generator(device="cuda").manual_seed(nf)
     mean = 1e5 * (0.5 + torch.rand((nz, nT, nf), generator=g, device="cuda", dtype=torch.float64))
     var = (mean * 0.01) ** 2
