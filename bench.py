@@ -453,7 +453,7 @@ def run_b200(args):
         achieved = cells_per_launch * FLOP_PER_CELL(nB) / (k_ms * 1e-3) * 1e-12
         grid_bytes = grid.grid.numel() * 8 + prior.numel() * 8
         roofline = {
-            "bound": "fp64", "kernel": "fused_like_kernel<%d,false>" % nB,
+            "bound": "fp64", "kernel": "fused_like_kernel<%d,false,2>" % nB,
             "bound_note": "FP64 vector (FMA) pipe: no stage is a dense contraction (tensor cores "
                           "not applicable) and HBM traffic is 3 orders of magnitude below its "
                           "roofline (BASELINE.json metric: % of FP64/HBM roofline)",
