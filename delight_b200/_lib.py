@@ -41,6 +41,7 @@ _SIGS = {
                             c_p, c_p, c_p, c_p],
     "dl_fused_chunk": [],
     "dl_fused_targets_per_cta": [],
+    "dl_fused_ctas_per_sm": [c_i, c_i],
     "dl_fused_padded_nz": [c_ll],
     "dl_fused_workspace_bytes": [c_ll, c_ll, c_ll, c_i, c_i],
     "dl_relayout_grid_dev": [c_ll, c_ll, c_ll, c_p, c_p, c_p, c_p],

@@ -157,13 +157,27 @@ def _as_dev(a):
     return torch.from_numpy(a).cuda()
 
 
-def _pick_nsplit(n_targets, nchunk, nT, sm_count):
+def _pick_nsplit(n_targets, nchunk, nT, sm_count, ctas_per_sm=2):
+    """Split of the training range over blockIdx.y.  With many CTAs (>= 8 waves) one split; with
+    few, the smallest split whose last wave is >= 95 % full (or the best one), so that e.g. 768
+    CTAs on 296 slots (2.6 waves, 87 %) become 2304 (7.8 waves, 97 %)."""
     tpc = _lib.lib().dl_fused_targets_per_cta()
     ctas = nchunk * ((n_targets + tpc - 1) // tpc)
-    want = 2 * sm_count          # 2 resident CTAs per SM
-    if ctas >= want:
+    slots = max(1, ctas_per_sm) * sm_count
+    if ctas >= 8 * slots:
         return 1
-    return int(max(1, min((want + ctas - 1) // ctas, max(1, nT // 32), 64)))
+    cap = int(max(1, min(max(1, nT // 32), 64)))
+    best, best_eff = 1, 0.0
+    for ns in range(1, cap + 1):
+        waves = ctas * ns / slots
+        eff = waves / np.ceil(waves)
+        if eff > best_eff + 1e-9:
+            best, best_eff = ns, eff
+        if eff >= 0.95:
+            return ns
+        if ctas * ns >= 8 * slots:
+            break
+    return best
 
 
 class FusedWorkspace:
@@ -292,11 +306,12 @@ def apply_fused(grid, prior, zgrid, targets, ell_hat=1.0, ell_var=1.0, K=0, want
             g_ev = torch.empty((n_g, K), dtype=torch.float64, device="cuda") if K > 0 else None
             g_evid = torch.empty((n_g, nT), dtype=torch.float64, device="cuda") \
                 if want_evid else None
-        ns_hint = nsplit or _pick_nsplit(n_g, nchunk, nT, ws.sm_count())
+        cps = L.dl_fused_ctas_per_sm(nf, int(zdep))
+        ns_hint = nsplit or _pick_nsplit(n_g, nchunk, nT, ws.sm_count(), cps)
         tile = ws.tile_size(n_g, nT, nz, ns_hint)
         for t0 in range(0, n_g, tile):
             n = min(tile, n_g - t0)
-            ns = nsplit or _pick_nsplit(n, nchunk, nT, ws.sm_count())
+            ns = nsplit or _pick_nsplit(n, nchunk, nT, ws.sm_count(), cps)
             nbytes = L.dl_fused_workspace_bytes(n, nT, nz, ns, int(want_evid or K == 0))
             buf = ws.get(nbytes)
             _lib.check(L.dl_like_fused_dev(

@@ -1140,6 +1140,12 @@ extern "C" {
 
 int dl_fused_chunk() { return FZC; }
 int dl_fused_targets_per_cta() { return FTPC; }
+// CTAs of the fused kernel that share an SM for nf bands (2 up to 13 bands, else 1)
+int dl_fused_ctas_per_sm(int nf, int zdep) {
+    if (nf < 1 || nf > MAXNF) return 0;
+    const int s = fused_stages(nf, zdep != 0);
+    return 2 * (fused_smem_bytes(nf, zdep != 0, s) + 1024) <= 228 * 1024 ? 2 : 1;
+}
 
 long long dl_fused_padded_nz(long long nz) { return (nz + FZC - 1) / FZC * FZC; }
 

@@ -121,6 +121,7 @@ int dl_kernel_grids_dev(long long nB, long long nzg, long long NC, long long NL,
  * variance 0).  Priors are [nT][nzp] (padding 0). */
 int dl_fused_chunk(void);
 int dl_fused_targets_per_cta(void);
+int dl_fused_ctas_per_sm(int nf, int zdep);   /* resident CTAs per SM for nf bands (launch sizing) */
 long long dl_fused_padded_nz(long long nz);
 long long dl_fused_workspace_bytes(long long nO, long long nT, long long nz, int nsplit,
                                    int evid_is_output_or_unused);
