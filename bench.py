@@ -36,9 +36,10 @@ Z_PRIOR_SIGMA = 0.5
 FLOP_PER_CELL = lambda nf: 27 * nf + 30     # SURVEY.md 8(d), fused path
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE fused_like_kernel launch at the default
 # configuration, from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` on a B200
-# (profiles/r1_fused_like_dram_traffic.csv): 6.94 GB read (1.6 GB grid + prior, re-read once per
-# CTA wave) + 19.37 GB written (per-z-chunk evidence partials, 12 x 16 B per (target, training)).
-NCU_TRAFFIC_BYTES_DEFAULT_CONFIG = 6937007104 + 19368152064
+# (profiles/r1_fused_like_dram_traffic.csv, grid 3756 x 4): 4.24 GB read (1.6 GB grid + prior,
+# re-read a few times over the launch, L2 hit rate 94 %) + 19.78 GB written (per-z-chunk evidence
+# partials, 12 x 16 B per (target, training), + the PDF partials).
+NCU_TRAFFIC_BYTES_DEFAULT_CONFIG = 4237682176 + 19782158336
 
 
 def workload_name(nO, nT, nz, nB):
