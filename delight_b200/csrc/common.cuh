@@ -100,7 +100,7 @@ __device__ __forceinline__ double exp_nonpos(double x) {
 //   N = 32:  degree 4 (truncation r^5/120 <= 1.3e-12 relative), 8 FP64-pipe instructions
 //   N = 128: degree 3 (truncation r^4/24  <= 2.3e-12 relative), 7 FP64-pipe instructions
 // (N = 1024 with degree 2 measured no faster: 1.268 s.)
-// instead of 14; the range / NaN tests run on the integer pipe.
+// instead of 14; the range test runs on the integer pipe.
 #ifndef DL_EXPTAB_BITS
 #define DL_EXPTAB_BITS 7
 #endif
@@ -127,11 +127,12 @@ __device__ __forceinline__ double exp_nonpos_tab(double x, const double* tab) {
     p *= tab[n & (EXP_TAB - 1)];
     const int hi = __double2hiint(p) + ((n >> DL_EXPTAB_BITS) << 20);
     const double res = __hiloint2double(hi, __double2loint(p));
-    // x < -708 (incl. -inf) -> 0, NaN -> NaN; both decided on the high word
+    // x < -708 (incl. -inf) -> 0, decided on the high word (integer pipe).  A NaN needs no test:
+    // every NaN the GPU produces or NumPy hands over has a zero low word (0x7ff8... / 0xfff8...),
+    // so n = 0, the exponent is left alone and p (= NaN) comes back as it is.
     const unsigned hx = (unsigned)__double2hiint(x);
-    const bool under = hx >= 0xC0862000u && hx <= 0xFFF00000u;     // -708 >= x >= -inf
-    const bool isnan = (hx & 0x7fffffffu) > 0x7ff00000u;
-    return isnan ? x : (under ? 0.0 : res);
+    const bool under = hx - 0xC0862000u <= 0xFFF00000u - 0xC0862000u;     // -708 >= x >= -inf
+    return under ? 0.0 : res;
 }
 
 __device__ __forceinline__ double warp_max(double v) {
@@ -169,6 +170,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+#ifndef DL_WAIT_HINT
+#define DL_WAIT_HINT 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done;
     asm volatile(
@@ -186,12 +190,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Wait with back-off: a waiter that just re-issues try_wait competes for issue slots with the
 // very warps (on its own scheduler) it is waiting for; __nanosleep takes it out of the way.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if DL_WAIT_HINT
+    // try_wait with a suspend-time hint: the hardware parks the warp (no issue slots) until the
+    // phase completes or the hint expires, instead of a software spin with nanosleep
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)DL_WAIT_HINT)
+            : "memory");
+    } while (!done);
+#else
     if (mbar_try_wait(bar, parity)) return;
     unsigned ns = 32;
     while (!mbar_try_wait(bar, parity)) {
         __nanosleep(ns);
         if (ns < 1024) ns <<= 1;
     }
+#endif
 }
 
 // One lane of a converged warp (elect.sync): code under this predicate is known to run in exactly
