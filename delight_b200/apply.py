@@ -168,8 +168,12 @@ def _pick_nsplit(n_targets, nchunk, nT, sm_count, ctas_per_sm=2):
     ctas = nchunk * ((n_targets + tpc - 1) // tpc)
     slots = max(1, ctas_per_sm) * sm_count
     cap = int(max(1, min(max(1, nT // 32), 64)))
-    best, best_eff = 1, 0.0
-    for ns in range(1, cap + 1):
+    fill = int(min(cap, max(1, slots // ctas)))           # splits that occupy (nearly) every slot
+    # beyond filling the machine a split must leave >= 600 training galaxies per CTA (the
+    # per-CTA prologue / epilogue costs about 80 steps)
+    cap = max(fill, min(cap, nT // 600))
+    best, best_eff = fill, 0.0
+    for ns in range(fill, cap + 1):
         waves = ctas * ns / slots
         eff = waves / np.ceil(waves)
         if eff > best_eff + 1e-9:

@@ -111,6 +111,9 @@ constexpr int MAXNF = 32;   // bands per target group
 // registers, which leaves room for redshift PAIRS there too.  Measured (2048 x 1500 x 1500 cells,
 // ms, REGNF 16 / ZJ 1 -> REGNF 8 / ZJ 2): nf 9: 64.7 -> 61.6, 13: 86.6 -> 81.4, 14: 128 -> 100,
 // 16: 136 -> 118, 28: 206 -> 195.
+#ifndef DL_GRPUNROLL
+#define DL_GRPUNROLL 2      // unroll factor of the z-group loop (2 = full for redshift pairs)
+#endif
 #ifndef DL_REGNF
 #define DL_REGNF 8
 #endif
@@ -462,7 +465,7 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
         const double* st = stage + s * ROWS * FZC;
         // fully unrolled for the register-cached variants; rolled for NF > REGNF (code size and
         // compile time: 4 x 4 x NF bands otherwise)
-#pragma unroll (NF > REGNF ? 1 : FZT / ZJ)
+#pragma unroll (NF > REGNF ? 1 : DL_GRPUNROLL)
         for (int grp = 0; grp < FZT / ZJ; ++grp) {
             const int zl = grp * 32 * ZJ + lane;      // cells: zl + 32 c, c < ZJ
             constexpr bool SMODEL = NF > REGNF;           // model values stay in the stage
