@@ -120,6 +120,7 @@ constexpr int MAXNF = 32;   // bands per target group
 #ifndef DL_SMODEL_ZJ
 #define DL_SMODEL_ZJ 2
 #endif
+constexpr int GRPUNROLL = DL_GRPUNROLL;   // (macros are not expanded inside #pragma unroll)
 constexpr int REGNF = DL_REGNF;   // up to here the model values of a z-group are cached in registers
 
 // per-target constants: [f][2] = (a' s, w') | [f][4] = (var', obs, obs^2, 0 (f = 0: c s)) |
@@ -465,7 +466,7 @@ __global__ void __launch_bounds__(FTHREADS, DL_MINB) fused_like_kernel(const Fus
         const double* st = stage + s * ROWS * FZC;
         // fully unrolled for the register-cached variants; rolled for NF > REGNF (code size and
         // compile time: 4 x 4 x NF bands otherwise)
-#pragma unroll (NF > REGNF ? 1 : DL_GRPUNROLL)
+#pragma unroll (NF > REGNF ? 1 : GRPUNROLL)
         for (int grp = 0; grp < FZT / ZJ; ++grp) {
             const int zl = grp * 32 * ZJ + lane;      // cells: zl + 32 c, c < ZJ
             constexpr bool SMODEL = NF > REGNF;           // model values stay in the stage
