@@ -413,8 +413,8 @@ def run_b200(args):
 
     def step_e2e():
         tg = apply.Targets.full(h_flux.numpy(), h_var.numpy())
-        tg._dev = {tuple(range(nB)): (h_flux.cuda(non_blocking=True),
-                                      h_var.cuda(non_blocking=True), None)}
+        tg._dev = {("nf", nB): (h_flux.cuda(non_blocking=True),
+                                h_var.cuda(non_blocking=True), None, None)}
         out = step_resident(tg)
         if world > 1:          # gather to rank 0 like the (commented) Gatherv calls, :201-217
             bufs = [torch.empty_like(out["pdf"]) for _ in range(world)] if rank == 0 else None

@@ -40,15 +40,16 @@ _SIGS = {
     "dl_kernel_grids_dev": [c_ll, c_ll, c_ll, c_ll, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
                             c_p, c_p, c_p, c_p],
     "dl_fused_chunk": [],
-    "dl_fused_targets_per_cta": [],
+    "dl_fused_targets_per_cta": [c_i, c_i],
     "dl_fused_ctas_per_sm": [c_i, c_i],
     "dl_fused_padded_nz": [c_ll],
-    "dl_fused_workspace_bytes": [c_ll, c_ll, c_ll, c_i, c_i],
+    "dl_fused_workspace_bytes": [c_ll, c_ll, c_ll, c_i],
     "dl_relayout_grid_dev": [c_ll, c_ll, c_ll, c_p, c_p, c_p, c_p],
     "dl_relayout_prior_dev": [c_ll, c_ll, c_p, c_p, c_p],
     "dl_zprior_dev": [c_ll, c_ll, c_p, c_p, c_d, c_p, c_p],
-    "dl_like_fused_dev": [c_ll, c_ll, c_ll, c_ll, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_d, c_d,
-                          c_p, c_p, c_d, c_i, c_i, c_p, c_ll, c_p, c_p, c_p, c_p, c_ll, c_p],
+    "dl_template_prior_dev": [c_ll, c_ll, c_p, c_p, c_p, c_p, c_p],
+    "dl_like_fused_dev": [c_ll, c_ll, c_ll, c_ll, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
+                          c_d, c_d, c_p, c_p, c_d, c_i, c_p, c_ll, c_p, c_p, c_p, c_p, c_ll, c_p],
     "dl_like_compressed_dev": [c_ll, c_ll, c_ll, c_ll, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_d, c_d,
                                c_p, c_p, c_d, c_i, c_p, c_i, c_p, c_ll, c_p, c_p],
     "dl_metrics_dev": [c_ll, c_ll, c_p, c_ll, c_p, c_p, c_p, c_p],

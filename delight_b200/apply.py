@@ -65,25 +65,22 @@ class Targets:
                        None if self.ztrue is None else self.ztrue[first:last])
 
     def to_device(self):
-        """Upload fluxes / variances once (per band group); later apply_fused calls on this
+        """Upload fluxes / variances once (per launch group); later apply_fused calls on this
         object start from HBM-resident inputs."""
         torch = _lib.require_cuda()
         self._dev = {}
-        for bands, idx in self.groups():
-            nf = len(bands)
-            self._dev[bands] = (
+        for key, nf, union, rows, idx in self.launch_groups():
+            self._dev[key] = (
                 torch.from_numpy(np.ascontiguousarray(self.fluxes[idx, :nf])).cuda(),
                 torch.from_numpy(np.ascontiguousarray(self.fluxes_var[idx, :nf])).cuda(),
-                torch.from_numpy(idx).cuda())
+                torch.from_numpy(idx).cuda(),
+                None if rows is None else torch.from_numpy(rows).cuda())
         return self
 
     def groups(self):
         """Yield (band tuple, indices) for targets sharing the same band list."""
-        if getattr(self, "_groups", None) is not None:
-            for g in self._groups:
-                yield g
-            return
-        self._groups = list(self._compute_groups())
+        if getattr(self, "_groups", None) is None:
+            self._groups = list(self._compute_groups())
         for g in self._groups:
             yield g
 
@@ -95,6 +92,39 @@ class Targets:
         for g in range(uniq.shape[0]):
             bands = tuple(int(b) for b in uniq[g] if b >= 0)
             yield bands, np.nonzero(inv == g)[0]
+
+    def launch_groups(self, per_band_set=False):
+        """Launch groups of the fused kernel: one per band COUNT.  Yields
+        (key, nf, union_bands, rows, indices): `rows` is None when every target of the group is
+        observed in exactly `union_bands`, else int32 [n, nf] with the position of each of the
+        target's bands (io.py:331-337 valid-band list) in `union_bands`.
+        per_band_set=True (or more than 32 distinct bands in a group): one group per band SET."""
+        cache = "_lgroups_set" if per_band_set else "_lgroups"
+        if getattr(self, cache, None) is None:
+            setattr(self, cache, list(self._compute_launch_groups(per_band_set)))
+        for g in getattr(self, cache):
+            yield g
+
+    def _compute_launch_groups(self, per_band_set):
+        if per_band_set:
+            for bands, idx in self.groups():
+                yield ("set",) + bands, len(bands), bands, None, idx
+            return
+        for nf in np.unique(self.nf):
+            nf = int(nf)
+            idx = np.nonzero(self.nf == nf)[0]
+            b = self.bands[idx, :nf]
+            if np.all(b == b[0]):
+                yield ("nf", nf), nf, tuple(int(x) for x in b[0]), None, idx
+                continue
+            union = np.unique(b)
+            if union.size > FUSED_MAX_BANDS:
+                for bands, sub in self.groups():
+                    if len(bands) == nf:
+                        yield ("set",) + bands, nf, bands, None, sub
+                continue
+            rows = np.searchsorted(union, b).astype(np.int32)
+            yield ("nf", nf), nf, tuple(int(x) for x in union), np.ascontiguousarray(rows), idx
 
 
 class ModelGrid:
@@ -158,36 +188,9 @@ def _as_dev(a):
     return torch.from_numpy(a).cuda()
 
 
-def _pick_nsplit(n_targets, nchunk, nT, sm_count, ctas_per_sm=2):
-    """Split of the training range over blockIdx.y: the smallest split whose last wave of CTAs
-    is >= 99 % full (else the best one found).  Measured: 768 CTAs on 296 slots (2.6 waves, 87 %)
-    -> split 3: 57.6 -> 51.6 ms; config 3 (12.7 waves, 97.6 %) -> split 4: 1.200 -> 1.175 s."""
-    if os.environ.get("DL_NSPLIT"):                      # tuning override
-        return int(os.environ["DL_NSPLIT"])
-    tpc = _lib.lib().dl_fused_targets_per_cta()
-    ctas = nchunk * ((n_targets + tpc - 1) // tpc)
-    slots = max(1, ctas_per_sm) * sm_count
-    cap = int(max(1, min(max(1, nT // 32), 64)))
-    fill = int(min(cap, max(1, slots // ctas)))           # splits that occupy (nearly) every slot
-    # beyond filling the machine a split must leave >= 600 training galaxies per CTA (the
-    # per-CTA prologue / epilogue costs about 80 steps)
-    cap = max(fill, min(cap, nT // 600))
-    best, best_eff = fill, 0.0
-    for ns in range(fill, cap + 1):
-        waves = ctas * ns / slots
-        eff = waves / np.ceil(waves)
-        if eff > best_eff + 1e-9:
-            best, best_eff = ns, eff
-        if eff >= 0.99:
-            return ns
-        if ctas * ns >= 64 * slots:
-            break
-    return best
-
-
 class FusedWorkspace:
-    """Re-usable device scratch for apply_fused (evidence partials dominate:
-    16 B x n_chunks x tile targets x nT)."""
+    """Re-usable device scratch for apply_fused (the raw evidences dominate:
+    8 B x tile targets x nT)."""
 
     def __init__(self, max_bytes=None):
         torch = _lib.require_cuda()
@@ -212,12 +215,13 @@ class FusedWorkspace:
             self.buf = torch.empty(int(nbytes), dtype=torch.uint8, device="cuda")
         return self.buf
 
-    def tile_size(self, nO, nT, nz, nsplit_hint=1):
+    def tile_size(self, nO, nT, nz, evid_external):
+        """Targets per call such that the scratch (8 B x (nzp + nT) + ~1.5 KB per target) fits."""
         L = _lib.lib()
-        tpc = L.dl_fused_targets_per_cta()
-        per = L.dl_fused_workspace_bytes(tpc, nT, nz, nsplit_hint, 0)
-        tile = max(tpc, (self.max_bytes // max(per, 1)) * tpc)
-        return int(min(tile, (nO + tpc - 1) // tpc * tpc))
+        unit = 64
+        per = L.dl_fused_workspace_bytes(unit, nT, nz, int(evid_external))
+        tile = max(unit, (self.max_bytes // max(per, 1)) * unit)
+        return int(min(tile, (nO + unit - 1) // unit * unit))
 
 
 def _metrics(L, torch, pdf, zg, targets, confidence_levels):
@@ -238,7 +242,7 @@ def _metrics(L, torch, pdf, zg, targets, confidence_levels):
 
 
 def apply_fused(grid, prior, zgrid, targets, ell_hat=1.0, ell_var=1.0, K=0, want_evid=False,
-                want_metrics=False, workspace=None, nsplit=None, out_device=False,
+                want_metrics=False, workspace=None, out_device=False,
                 confidence_levels=None, cov_scale=1.0):
     """Likelihood + PDF + evidences + top-K for all `targets` against the whole model grid.
 
@@ -247,6 +251,8 @@ def apply_fused(grid, prior, zgrid, targets, ell_hat=1.0, ell_var=1.0, K=0, want
     cov_scale: factor on the model variance (delight-optimize.py:122 passes V_C * model_covar).
     confidence_levels (with want_metrics): the cfg's confidenceLevels; the metrics then carry the
     reference's 7 + nCL columns of computeMetrics (utils.py:213-227) followed by the argmax index.
+    Targets with different valid-band lists (io.py:331-337) share a launch as long as they have
+    the same NUMBER of bands: one kernel launch per band count, not per band set.
     Returns dict(pdf [nO, nz], top_idx [nO, K] int64, top_ev [nO, K], evid [nO, nT] | None,
     metrics [nO, 8 (+ nCL)] | None) as NumPy arrays (or CUDA tensors with out_device=True).
     """
@@ -254,7 +260,8 @@ def apply_fused(grid, prior, zgrid, targets, ell_hat=1.0, ell_var=1.0, K=0, want
     L = _lib.lib()
     nO = len(targets)
     nT, nB, nz = grid.nT, grid.nB, grid.nz
-    if targets.fluxes.shape[1] > nB and targets.bands.max() >= nB:
+    valid = np.arange(targets.bands.shape[1])[None, :] < targets.nf[:, None]
+    if nO and targets.bands[valid].max() >= nB:
         raise ValueError("target band index outside the model grid")
     if K > nT:
         raise ValueError("Ncompress (K=%d) exceeds the number of training galaxies (%d)" % (K, nT))
@@ -283,25 +290,25 @@ def apply_fused(grid, prior, zgrid, targets, ell_hat=1.0, ell_var=1.0, K=0, want
     top_idx = torch.empty((nO, K), dtype=torch.int64, device="cuda") if K > 0 else None
     top_ev = torch.empty((nO, K), dtype=torch.float64, device="cuda") if K > 0 else None
     evid = torch.empty((nO, nT), dtype=torch.float64, device="cuda") if want_evid else None
-    nchunk = grid.nzp // L.dl_fused_chunk()
     launches = 0
 
-    for bands, idx in targets.groups():
-        nf = len(bands)
+    # per-target band lists are not combined with z-dependent ell priors in the kernel
+    for key, nf, union, rows, idx in targets.launch_groups(per_band_set=zdep):
         if nf > FUSED_MAX_BANDS:
             raise _lib.DelightB200Error("fused likelihood supports up to %d bands per target, "
                                         "got %d" % (FUSED_MAX_BANDS, nf))
         single = idx.size == nO
         cached = getattr(targets, "_dev", None)
-        if cached is not None and bands in cached:
-            obs, var, didx = cached[bands]
+        if cached is not None and key in cached:
+            obs, var, didx, drows = cached[key]
         else:
             obs_h = targets.fluxes[idx, :nf] if not single else targets.fluxes[:, :nf]
             var_h = targets.fluxes_var[idx, :nf] if not single else targets.fluxes_var[:, :nf]
             obs = torch.from_numpy(np.ascontiguousarray(obs_h)).cuda(non_blocking=True)
             var = torch.from_numpy(np.ascontiguousarray(var_h)).cuda(non_blocking=True)
             didx = None
-        bands_c = (ctypes.c_int * nf)(*bands)
+            drows = None if rows is None else torch.from_numpy(rows).cuda(non_blocking=True)
+        union_c = (ctypes.c_int * len(union))(*union)
         n_g = idx.size
         if single:
             g_pdf, g_idx, g_ev, g_evid = pdf, top_idx, top_ev, evid
@@ -311,18 +318,18 @@ def apply_fused(grid, prior, zgrid, targets, ell_hat=1.0, ell_var=1.0, K=0, want
             g_ev = torch.empty((n_g, K), dtype=torch.float64, device="cuda") if K > 0 else None
             g_evid = torch.empty((n_g, nT), dtype=torch.float64, device="cuda") \
                 if want_evid else None
-        cps = L.dl_fused_ctas_per_sm(nf, int(zdep))
-        ns_hint = nsplit or _pick_nsplit(n_g, nchunk, nT, ws.sm_count(), cps)
-        tile = ws.tile_size(n_g, nT, nz, ns_hint)
+        ext = int(want_evid or K == 0)
+        tile = ws.tile_size(n_g, nT, nz, ext)
         for t0 in range(0, n_g, tile):
             n = min(tile, n_g - t0)
-            ns = nsplit or _pick_nsplit(n, nchunk, nT, ws.sm_count(), cps)
-            nbytes = L.dl_fused_workspace_bytes(n, nT, nz, ns, int(want_evid or K == 0))
+            nbytes = L.dl_fused_workspace_bytes(n, nT, nz, ext)
             buf = ws.get(nbytes)
             _lib.check(L.dl_like_fused_dev(
-                n, nT, nz, nB, nf, bands_c, _lib.ptr(obs[t0:t0 + n]), _lib.ptr(var[t0:t0 + n]),
+                n, nT, nz, nB, nf, len(union), union_c,
+                _lib.ptr(drows[t0:t0 + n]) if drows is not None else None,
+                _lib.ptr(obs[t0:t0 + n]), _lib.ptr(var[t0:t0 + n]),
                 _lib.ptr(grid.grid), _lib.ptr(prior), _lib.ptr(zg), ehs, evs, _lib.ptr(eh),
-                _lib.ptr(ev), float(cov_scale), ns, K, _lib.ptr(g_pdf[t0:t0 + n]), nz,
+                _lib.ptr(ev), float(cov_scale), K, _lib.ptr(g_pdf[t0:t0 + n]), nz,
                 _lib.ptr(g_evid[t0:t0 + n]) if g_evid is not None else None,
                 _lib.ptr(g_idx[t0:t0 + n]) if K > 0 else None,
                 _lib.ptr(g_ev[t0:t0 + n]) if K > 0 else None,
@@ -374,7 +381,8 @@ def apply_compressed(grid, prior, zgrid, targets, indices, ell_hat=1.0, ell_var=
     K = indices.shape[1]
     if K < 1:
         raise ValueError("need at least one stored index per target")
-    if targets.fluxes.shape[1] > nB and targets.bands.max() >= nB:
+    valid = np.arange(targets.bands.shape[1])[None, :] < targets.nf[:, None]
+    if nO and targets.bands[valid].max() >= nB:
         raise ValueError("target band index outside the model grid")
     # the in1d mask as a sorted, de-duplicated, -1 padded index list per target
     big = np.iinfo(np.int64).max

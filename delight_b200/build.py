@@ -9,7 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdelight_b200.so")
-SOURCES = ["capi.cu", "like_dropin.cu", "like_fused.cu", "like_compressed.cu", "kernelparts.cu",
+SOURCES = ["capi.cu", "like_dropin.cu", "like_fused.cu", "like_fused_t0.cu", "like_fused_t1.cu",
+           "like_fused_t2.cu", "like_fused_t3.cu", "like_compressed.cu", "kernelparts.cu",
            "gp_batched.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=true", "-ccbin", "/usr/bin/g++"]

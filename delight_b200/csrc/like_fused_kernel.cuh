@@ -1,0 +1,589 @@
+// Fused photo-z likelihood for a batch of targets (subsystem 1 of the north star): the kernel.
+//
+// Replaces the per-target host loop of scripts/delight-apply.py:114-162:
+//     approx_flux_likelihood_cy (delight/utils_cy.pyx:83-128)  ->  like[nz][nT]
+//     like *= prior; pdf = sum_t like; evid = trapz_z like; top-K by evidence
+// The like[nz][nT] array of a target never exists in HBM, and (round 2) neither do per-z-chunk
+// evidence partials: one CTA owns ALL redshifts of its cells.
+//
+// Work decomposition (B200: 148 SMs, FP64 pipe = 16 lanes / SMSP, 227 KB smem / SM)
+//   unit     = one tile of targets (32 / 64)  x  one block of TT training galaxies  x  ALL z
+//   CTA      = one unit; warps own 4 targets each, warp 0 also drives TMA
+//              config 0 (<= 8 bands, homogeneous band set): 8 warps, 128-redshift stages, 2 CTAs/SM
+//              config 1 (more bands / per-target band lists): 16 warps, 64-redshift stages, 1 CTA/SM
+//   step     = (z-chunk c, training galaxy k): one pipeline stage of 2 nU + 2 rows (nU band means,
+//              nU band variances, the prior row, the trapezoid-weight row) of FZC doubles, fetched
+//              with 1-D TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx) into a
+//              full/empty mbarrier ring; steps run chunk-major (c outer, k inner)
+//   lane     = FZC/32 redshifts of the chunk (z = z0 + 32 j + lane) -> conflict-free smem rows
+//   compute  = per (target, training galaxy, z) cell, all in FP64 on the vector pipe: pass 0 with
+//              the observed variances only, one reciprocal for the luminosity scale, pass 1 with
+//              the model variance folded in (one reciprocal per PAIR of bands), chi2,
+//              (prod var * FTT)^-1/2 by one rsqrt, one table-based exp.  No log, no division.
+//   reduce   = PDF: shared-memory accumulator per (target, z of the chunk), flushed with
+//              red.global.add.f64 at the end of every chunk (the PDF rows of the ~150 tiles in
+//              flight stay in L2);  evidence: warp sum per step added to a shared-memory
+//              accumulator per (target, k), complete after the last chunk, stored ONCE.
+//
+// Normalisation.  The reference subtracts the GLOBAL max log-likelihood of a target before exp
+// (utils_cy.pyx:120-128).  Here every target gets a fixed ANCHOR exponent A before the main
+// pass -- the max of -chi2/2 over a strided sample of training galaxies (the same kernel in
+// SAMPLE mode, < 1 % of the work) -- folded into a per-target constant, so that every partial
+// sum of every CTA is expressed in the same units and can simply be added.  The kernel tracks
+// max(v) per target (the final divisor: results equal exp(L - max L) up to rounding) and whether
+// any cell exceeded A by more than e^500; such targets (never seen with photometric S/N < 100)
+// are recomputed by a rescue pass with the exact max as anchor (dl_like_fused_dev).
+#pragma once
+#include "common.cuh"
+
+namespace dl {
+
+constexpr int FTO = 4;        // targets per warp
+constexpr int MAXNF = 32;     // bands per target
+constexpr int REGNF = 8;      // up to here the model values of a z-group are cached in registers
+constexpr int ZJ = 2;         // redshifts a lane processes jointly (independent dependency chains)
+#ifndef DL_STAGES
+#define DL_STAGES 4
+#endif
+#ifndef DL_PREF
+#define DL_PREF 2
+#endif
+#ifndef DL_CFG1_NF
+#define DL_CFG1_NF 9          // homogeneous band sets from here on use config 1
+#endif
+
+enum { MODE_MAIN = 0, MODE_SAMPLE = 1 };
+
+__host__ __device__ constexpr int cfg_of(int nf, bool het) { return (het || nf >= DL_CFG1_NF) ? 1 : 0; }
+__host__ __device__ constexpr int cfg_warps(int cfg) { return cfg ? 16 : 8; }
+__host__ __device__ constexpr int cfg_fzc(int cfg) { return cfg ? 64 : 128; }
+__host__ __device__ constexpr int cfg_tt(int cfg) { return cfg ? 32 : 64; }     // default t-block
+
+// per-target constants (doubles), s = sqrt(cov_scale / c), c = power of two near the variances:
+//   [0, 2NF)      (a_f s, w_f)          pass 0:  a = obs / var', w = 1 / var'
+//   [2NF, 4NF)    (var'_f, obs_f)       pass 1
+//   [4NF, 5NF)    obs_f^2
+//   5NF + TC_*    scalars below
+//   then (per-target band lists only) NF int32 element offsets of the target's band rows in a stage
+enum { TC_HC = 0, TC_POT0, TC_POT, TC_PTT, TC_POO, TC_C, TC_CS, TC_XOFF, TC_POO0, TC_SPARE, TC_NCONST };
+__host__ __device__ constexpr int tc_stride(int nf, bool het) {
+    return (5 * nf + TC_NCONST + (het ? (nf + 1) / 2 : 0) + 1) & ~1;
+}
+
+struct FusedParams {
+    const double* grid;        // [nT][2*nB][nzp]  rows 0..nB-1 mean, nB..2nB-1 variance
+    const double* prior;       // [nT][nzp]
+    const double* tconst;      // [nO][tc_stride]
+    const double* wz;          // [nzp] trapezoid weights (0 in the padding)
+    const double* zdep;        // [4][nzp]: ell_hat/ell_var, 1/ell_var, ell_hat^2/ell_var, ell_var
+    double* pdf_acc;           // [nO][nzp]   zero-initialised, accumulated with red.add
+    double* evid;              // [nO][nT]    raw evidences (units of the anchor)
+    unsigned long long* Vbits; // [nO] bits of max v (non-negative doubles order like integers)
+    unsigned long long* Akey;  // [nO] SAMPLE mode: ordered key of max x
+    int* flag;                 // [nO] MAIN: 1 = a cell exceeded the anchor by > e^500
+    int* nflag;                // [1]  != 0 if any flag is set
+    int bands[MAXNF];          // band rows staged per step (the union of the targets' bands)
+    int nU;                    // how many
+    int nB, nz, nzp, nT, nO;
+    int TT, nTB;               // training galaxies per unit, units per target tile
+    int nTlist, t_stride;      // the units cover t = i * t_stride, i < nTlist
+    int nTiles, G;             // target tiles, tiles per L2 group
+    int stages;                // TMA ring depth
+    int rescue;                // 1: only tiles with flagged targets run; only those are stored
+};
+
+__host__ __device__ inline size_t fused_smem_bytes(int cfg, int nf, bool het, bool zdep, int nU,
+                                                   int stages, int TT) {
+    const int fzc = cfg_fzc(cfg), ftpc = cfg_warps(cfg) * FTO;
+    const int rows = 2 * nU + 2 + (zdep ? 4 : 0);
+    return sizeof(double) * ((size_t)stages * rows * fzc + (size_t)ftpc * fzc +
+                             (size_t)ftpc * tc_stride(nf, het) + (size_t)ftpc * TT + EXP_TAB + ftpc) +
+           2 * stages * sizeof(uint64_t);
+}
+
+// x = -chi2/2 - A (in the target's units, + the padding mask) and y = (det)^-1/2 of ZJ cells of
+// one target against one training galaxy: utils_cy.pyx:98-118 restructured (header comment).
+// Where the band means / variances of the cells come from: registers (loaded once per z-group and
+// reused by the warp's targets; homogeneous band sets up to REGNF bands) or the stage in shared
+// memory (more bands: 2 NF ZJ doubles do not fit the register budget; per-target band lists: the
+// rows differ from target to target).
+template <int NF>
+struct RegModel {
+    const double (&mm)[ZJ][NF];
+    const double (&cc)[ZJ][NF];
+    __device__ __forceinline__ double m(int c, int f) const { return mm[c][f]; }
+    __device__ __forceinline__ double cv(int c, int f) const { return cc[c][f]; }
+};
+template <int NF, int FZC>
+struct SmemModel {
+    const double* stz;      // stage + the lane's first redshift
+    __device__ __forceinline__ double m(int c, int f) const { return stz[f * FZC + 32 * c]; }
+    __device__ __forceinline__ double cv(int c, int f) const { return stz[(NF + f) * FZC + 32 * c]; }
+};
+template <int NF, int FZC>
+struct SmemModelHet {
+    const double* stz;      // stage + the lane's first redshift
+    const int* off;         // the target's NF row offsets (elements) into a stage
+    int var0;               // nU * FZC: first variance row
+    __device__ __forceinline__ double m(int c, int f) const { return stz[off[f] + 32 * c]; }
+    __device__ __forceinline__ double cv(int c, int f) const { return stz[off[f] + var0 + 32 * c]; }
+};
+
+template <int NF, class Model>
+__device__ __forceinline__ void cells_xy(const double* tc, const Model md, const double (&pOT0)[ZJ],
+                                         const double (&pOT)[ZJ], const double (&pTT)[ZJ],
+                                         const double (&pOO)[ZJ], const double (&zev)[ZJ],
+                                         const double (&xmask)[ZJ], double (&x)[ZJ],
+                                         double (&y)[ZJ]) {
+    const double2* tc0 = reinterpret_cast<const double2*>(tc);             // (a s, w)
+    const double2* tc1 = reinterpret_cast<const double2*>(tc + 2 * NF);    // (var', obs)
+    const double* tc2 = tc + 4 * NF;                                       // obs^2
+    const double hc = tc[5 * NF + TC_HC];
+    // pass 0: observed variances only (utils_cy.pyx:101-113 with ellML = 0)
+    double fot[ZJ], ftt[ZJ], foo[ZJ], P[ZJ], P2[ZJ], e2[ZJ];   // det = P * P2 (P2 only for NF > REGNF)
+#pragma unroll
+    for (int c = 0; c < ZJ; ++c) { fot[c] = pOT0[c]; ftt[c] = pTT[c]; }
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        const double2 aw = tc0[f];
+#pragma unroll
+        for (int c = 0; c < ZJ; ++c) {
+            const double mf = md.m(c, f);
+            const double tw = mf * aw.y;
+            fot[c] = fma(mf, aw.x, fot[c]);
+            ftt[c] = fma(tw, mf, ftt[c]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < ZJ; ++c) {
+        const double ell = fot[c] * rcp_fast(ftt[c]);     // ellML * sqrt(cov_scale / c)
+        e2[c] = ell * ell;
+        fot[c] = pOT[c]; ftt[c] = pTT[c]; foo[c] = pOO[c]; P[c] = zev[c]; P2[c] = 1.0;
+    }
+    // pass 1: variance inflated by ell^2 * model variance (utils_cy.pyx:107-112).  Bands in
+    // pairs: ONE reciprocal of the product of the pair's variances gives both 1/var
+    // (r_a = var_b / (var_a var_b)) and the pair's factor of the determinant: 9 FP64
+    // instructions + 1 MUFU per pair instead of 10 + 2.
+    auto acc = [&](int c, int f, double r, double ob) {
+        const double mf = md.m(c, f);
+        const double tm = mf * r;
+        fot[c] = fma(tm, ob, fot[c]);
+        ftt[c] = fma(tm, mf, ftt[c]);
+        foo[c] = fma(tc2[f], r, foo[c]);
+    };
+    constexpr int NG = (NF / 2) * 2;
+#pragma unroll
+    for (int f = 0; f < NG; f += 2) {
+        const double2 voa = tc1[f], vob = tc1[f + 1];
+#pragma unroll
+        for (int c = 0; c < ZJ; ++c) {
+            const double va = fma(e2[c], md.cv(c, f), voa.x);
+            const double vb = fma(e2[c], md.cv(c, f + 1), vob.x);
+            const double pab = va * vb;
+            const double ri = rcp_fast(pab);
+            acc(c, f, vb * ri, voa.y);
+            acc(c, f + 1, va * ri, vob.y);
+            if (NF > REGNF && f >= NF / 2) P2[c] *= pab; else P[c] *= pab;
+        }
+    }
+    if (NF - NG == 1) {
+        constexpr int f = NF - 1;
+        const double2 vo = tc1[f];
+#pragma unroll
+        for (int c = 0; c < ZJ; ++c) {
+            const double var = fma(e2[c], md.cv(c, f), vo.x);
+            acc(c, f, rcp_fast(var), vo.y);
+            if (NF > REGNF) P2[c] *= var; else P[c] *= var;
+        }
+    }
+    // chi2 and (det)^-1/2 (utils_cy.pyx:111-118)
+#pragma unroll
+    for (int c = 0; c < ZJ; ++c) {
+        double rF;
+        if (NF > REGNF) {
+            // many bands: the determinant is kept as two factors so that it cannot leave the
+            // double range (model variance >> observed variance in every band), and 1/FTT has
+            // its own reciprocal
+            y[c] = rsqrt_fast(P[c] * ftt[c]) * rsqrt_fast(P2[c]);
+            rF = rcp_fast(ftt[c]);
+        } else {
+            y[c] = rsqrt_fast(P[c] * ftt[c]);
+            rF = (y[c] * y[c]) * P[c];               // 1 / FTT
+        }
+        const double chi2 = fma(-(fot[c] * rF), fot[c], foo[c]);
+        x[c] = fma(hc, chi2, xmask[c]);              // -chi2/2 - A in the target's units
+    }
+}
+
+// 500.0 = 0x407F4000'00000000: a cell more than e^500 above the anchor flags its target
+constexpr int HI_OVERFLOW = 0x407F4000;
+
+template <int NF, bool ZDEP, bool HET, int MODE>
+__global__ void __launch_bounds__(cfg_warps(cfg_of(NF, HET)) * 32, cfg_of(NF, HET) ? 1 : 2)
+fused_like_kernel(const FusedParams p) {
+    constexpr int CFG = cfg_of(NF, HET);
+    constexpr int FW = cfg_warps(CFG), FZC = cfg_fzc(CFG), FZT = FZC / 32;
+    constexpr int FTPC = FW * FTO, THREADS = FW * 32;
+    constexpr int TCS = tc_stride(NF, HET);
+    constexpr bool SMODEL = HET || NF > REGNF;        // model values stay in the stage
+    constexpr bool SAMPLE = MODE == MODE_SAMPLE;
+    const int nU = HET ? p.nU : NF;
+    const int ROWS = 2 * nU + 2 + (ZDEP ? 4 : 0);
+    const int STG = p.stages;
+    const int PREF = (DL_PREF < STG - 2 ? DL_PREF : STG - 2) > 1 ? (DL_PREF < STG - 2 ? DL_PREF : STG - 2) : 1;
+    const int TTs = p.TT;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* stage = reinterpret_cast<double*>(smem_raw);            // [STG][ROWS][FZC]
+    double* pdf_sm = stage + (size_t)STG * ROWS * FZC;              // [FTPC][FZC]
+    double* tc_sm = pdf_sm + FTPC * FZC;                            // [FTPC][TCS]
+    double* E_sm = tc_sm + FTPC * TCS;                              // [FTPC][TT]
+    double* etab_w = E_sm + (size_t)FTPC * TTs;                     // [EXP_TAB]
+    unsigned long long* V_sm = reinterpret_cast<unsigned long long*>(etab_w + EXP_TAB);   // [FTPC]
+    uint64_t* full = reinterpret_cast<uint64_t*>(V_sm + FTPC);
+    uint64_t* empty = full + STG;
+    const double* etab = etab_w;
+
+    // unit -> (target tile, training block).  Tiles are grouped G at a time and, inside a group,
+    // run tile-fastest / block-slowest: the CTAs in flight then share a few training blocks (the
+    // model grid is read from HBM about nTiles / G times in all) and the PDF rows of one group
+    // (G x tile x nzp x 8 B) stay in L2 between the flushes of successive blocks.
+    int tile, tb;
+    {
+        const int u = blockIdx.x;
+        const int gsz = p.G * p.nTB;
+        const int grp = u / gsz, r = u - grp * gsz;
+        const int left = p.nTiles - grp * p.G;
+        const int tig = left < p.G ? left : p.G;
+        tb = r / tig;
+        tile = grp * p.G + (r - tb * tig);
+    }
+    const int ts0 = tb * p.TT;
+    const int tcount = (p.nTlist - ts0) < p.TT ? (p.nTlist - ts0) : p.TT;
+    const int nchunk = p.nzp / FZC;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (p.rescue) {
+        // rescue passes: only tiles that hold a flagged target do anything
+        int any = 0;
+        if (*p.nflag != 0)
+            for (int i = threadIdx.x; i < FTPC; i += THREADS) {
+                const int o = tile * FTPC + i;
+                any |= (o < p.nO) ? p.flag[o] : 0;
+            }
+        if (!__syncthreads_or(any)) return;
+    }
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STG; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], FW);
+        }
+        mbar_fence_init();
+    }
+    for (int i = threadIdx.x; i < FTPC * TCS; i += THREADS) {
+        int o = tile * FTPC + i / TCS;
+        o = o < p.nO ? o : p.nO - 1;
+        tc_sm[i] = p.tconst[(size_t)o * TCS + (i % TCS)];
+    }
+    if (!SAMPLE) {
+        exp_tab_init(etab_w, threadIdx.x, THREADS);
+        for (int i = threadIdx.x; i < FTPC * FZC; i += THREADS) pdf_sm[i] = 0.0;
+        for (int i = threadIdx.x; i < FTPC * TTs; i += THREADS) E_sm[i] = 0.0;
+        for (int i = threadIdx.x; i < FTPC; i += THREADS) {
+            const int o = tile * FTPC + i;
+            // any lower bound of the final max is fine as a start; never below the smallest
+            // normal double, so that cells that underflow (v = 0) do not take the slow path
+            const unsigned long long v0 = o < p.nO ? p.Vbits[o] : 0ull;
+            V_sm[i] = v0 > 0x0010000000000000ull ? v0 : 0x0010000000000000ull;
+        }
+    }
+    __syncthreads();
+
+    // ---------------------------------------------------------------------- TMA producer
+    // No dedicated producer warp (it would cost 32 registers/thread of occupancy): warp 0
+    // refills, before it computes step `it`, the stage every warp released PREF steps ago.
+    // The WHOLE warp polls the barrier and only the straight-line copy issue is single-lane
+    // code (elect.sync): a lane spinning alone leaves its warp split for good (tools/ubench_wait.cu).
+    // The producer keeps no cursor of its own: the step it issues is always `ahead` steps past
+    // the consumer cursor (cs, cph, k, chunk) of the same warp.
+    int cs = 0, cph = 0, k = 0, chunk = 0;        // consumer cursor: stage, phase, k, z-chunk
+    auto issue_ahead = [&](int ahead) {
+        int s = cs + ahead, ph = cph;
+        if (s >= STG) { s -= STG; ph ^= 1; }
+        int pk = k + ahead, pc = chunk;
+        while (pk >= tcount) { pk -= tcount; ++pc; }
+        if (pc >= nchunk) return;                 // past the last step (warp-uniform)
+        mbar_wait(&empty[s], ph ^ 1);
+        if (elect_one()) {
+            const size_t row = (size_t)p.nzp;
+            const size_t t = (size_t)(ts0 + pk) * p.t_stride;
+            const int z0 = pc * FZC;
+            mbar_arrive_expect_tx(&full[s], ROWS * FZC * sizeof(double));
+            const double* gt = p.grid + t * 2 * p.nB * row + z0;
+            double* dst = stage + (size_t)s * ROWS * FZC;
+            if (HET) {
+                for (int f = 0; f < nU; ++f) {
+                    tma_bulk_g2s(dst + f * FZC, gt + (size_t)p.bands[f] * row,
+                                 FZC * sizeof(double), &full[s]);
+                    tma_bulk_g2s(dst + (nU + f) * FZC, gt + (size_t)(p.nB + p.bands[f]) * row,
+                                 FZC * sizeof(double), &full[s]);
+                }
+            } else {
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    tma_bulk_g2s(dst + f * FZC, gt + (size_t)p.bands[f] * row,
+                                 FZC * sizeof(double), &full[s]);
+                    tma_bulk_g2s(dst + (NF + f) * FZC, gt + (size_t)(p.nB + p.bands[f]) * row,
+                                 FZC * sizeof(double), &full[s]);
+                }
+            }
+            tma_bulk_g2s(dst + 2 * nU * FZC, p.prior + t * row + z0, FZC * sizeof(double),
+                         &full[s]);
+            tma_bulk_g2s(dst + (2 * nU + 1) * FZC, p.wz + z0, FZC * sizeof(double), &full[s]);
+            if (ZDEP) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    tma_bulk_g2s(dst + (2 * nU + 2 + q) * FZC, p.zdep + (size_t)q * row + z0,
+                                 FZC * sizeof(double), &full[s]);
+            }
+        }
+        __syncwarp();
+    };
+    if (warp == 0)
+        for (int j = 0; j < PREF; ++j) issue_ahead(j);
+
+    // ---------------------------------------------------------------------- compute
+    // Each lane works on PAIRS of redshifts (z, z+32) of the chunk for one target at a time:
+    // the target's constants are fetched once (broadcast LDS.128) for two cells and every
+    // statement below carries two independent dependency chains for the FP64 pipe.
+    double E[FTO];
+#pragma unroll
+    for (int o = 0; o < FTO; ++o) E[o] = SAMPLE ? -INFINITY : 0.0;
+    int ovf = (int)0x80000000;                    // running max of the high words of x
+    const int tfirst = warp * FTO;
+    const double* tcw = tc_sm + tfirst * TCS;
+    double* pdfw = pdf_sm + tfirst * FZC;
+    const int og0 = tile * FTPC + tfirst;
+    const int var0 = nU * FZC;
+
+    while (chunk < nchunk) {
+        if (warp == 0) issue_ahead(PREF);                                 // warp-uniform
+        mbar_wait(&full[cs], cph);
+        const double* st = stage + (size_t)cs * ROWS * FZC;
+        const int z0 = chunk * FZC;
+        // fully unrolled for the register-cached variants; rolled when the model values stay in
+        // the stage (code size and compile time: 4 x NF bands x groups otherwise) and in SAMPLE
+        // mode (no branch separates the targets there: unrolled, the scheduler interleaves all
+        // eight target visits of a step and spills 1.7 KB per thread)
+#pragma unroll (SMODEL ? 1 : FZT / ZJ)
+        for (int grp = 0; grp < FZT / ZJ; ++grp) {
+            const int zl = grp * 32 * ZJ + lane;      // cells: zl + 32 c, c < ZJ
+            constexpr int RN = SMODEL ? 1 : NF;
+            double m[ZJ][RN], cv[ZJ][RN];
+            if (!SMODEL) {
+#pragma unroll
+                for (int f = 0; f < RN; ++f) {
+#pragma unroll
+                    for (int c = 0; c < ZJ; ++c) {
+                        m[c][f] = st[f * FZC + zl + 32 * c];
+                        cv[c][f] = st[(NF + f) * FZC + zl + 32 * c];
+                    }
+                }
+            }
+            double pr[ZJ], wzv[ZJ], xmask[ZJ], zot[ZJ], ztt[ZJ], zoo[ZJ], zev[ZJ];
+#pragma unroll
+            for (int c = 0; c < ZJ; ++c) {
+                pr[c] = st[2 * var0 + zl + 32 * c];
+                wzv[c] = st[2 * var0 + FZC + zl + 32 * c];
+                // padded redshifts get x = -inf: they never count for the max and contribute 0
+                xmask[c] = ((z0 + zl + 32 * c) < p.nz) ? 0.0 : -INFINITY;
+                zot[c] = ztt[c] = zoo[c] = 0.0; zev[c] = 1.0;
+                if (ZDEP) {
+                    const double* zd = st + 2 * var0 + 2 * FZC + zl + 32 * c;
+                    zot[c] = zd[0]; ztt[c] = zd[FZC]; zoo[c] = zd[2 * FZC]; zev[c] = zd[3 * FZC];
+                }
+            }
+#pragma unroll (SMODEL || SAMPLE ? 1 : FTO)
+            for (int o = 0; o < FTO; ++o) {
+                // E[] is rotated once per target so the loop can stay rolled with the
+                // accumulators in registers (FTO rotations restore the order)
+                double Eo = E[0];
+                const double* tc = tcw + o * TCS;
+                const double* tk = tc + 5 * NF;
+                double pOT0[ZJ], pOT[ZJ], pTT[ZJ], pOO[ZJ], xm[ZJ];
+#pragma unroll
+                for (int c = 0; c < ZJ; ++c) {
+                    if (ZDEP) {
+                        const double cc = tk[TC_C];
+                        pOT0[c] = tk[TC_CS] * zot[c];
+                        pOT[c] = cc * zot[c]; pTT[c] = cc * ztt[c]; pOO[c] = cc * zoo[c];
+                        xm[c] = SAMPLE ? xmask[c] : xmask[c] + tk[TC_XOFF];     // -A
+                    } else {
+                        // the anchor is folded into the constant term of FOO (TC_POO); the
+                        // sampling pass measures the un-anchored exponent (TC_POO0)
+                        pOT0[c] = tk[TC_POT0];
+                        pOT[c] = tk[TC_POT]; pTT[c] = tk[TC_PTT];
+                        pOO[c] = tk[SAMPLE ? TC_POO0 : TC_POO];
+                        xm[c] = xmask[c];
+                    }
+                }
+                double x[ZJ], y[ZJ];
+                if constexpr (HET)
+                    cells_xy<NF>(tc, SmemModelHet<NF, FZC>{st + zl,
+                                     reinterpret_cast<const int*>(tk + TC_NCONST), var0},
+                                 pOT0, pOT, pTT, pOO, zev, xm, x, y);
+                else if constexpr (SMODEL)
+                    cells_xy<NF>(tc, SmemModel<NF, FZC>{st + zl}, pOT0, pOT, pTT, pOO, zev, xm, x, y);
+                else
+                    cells_xy<NF>(tc, RegModel<NF>{m, cv}, pOT0, pOT, pTT, pOO, zev, xm, x, y);
+                if constexpr (SAMPLE) {
+                    double xl = x[0];
+#pragma unroll
+                    for (int c = 1; c < ZJ; ++c) xl = fmax(xl, x[c]);
+                    Eo = fmax(Eo, xl);
+                } else {
+                    double v[ZJ];
+                    int vh = 0;
+#pragma unroll
+                    for (int c = 0; c < ZJ; ++c) {
+                        v[c] = exp_nonpos_tab(x[c], etab) * y[c];          // :118,128
+                        ovf = max(ovf, __double2hiint(x[c]));
+                        vh = max(vh, __double2hiint(v[c]));
+                    }
+                    // running max of v (the final divisor), kept per target in shared memory:
+                    // only the high word is read here; the rare record-breaking cells take the
+                    // slow path (O(log) times per lane)
+                    if (vh >= reinterpret_cast<const int*>(V_sm + tfirst + o)[1]) {
+#pragma unroll
+                        for (int c = 0; c < ZJ; ++c)
+                            if (v[c] == v[c])
+                                atomicMax(V_sm + tfirst + o,
+                                          (unsigned long long)__double_as_longlong(v[c]));
+                    }
+                    // prior, PDF and evidence accumulation  (delight-apply.py:145-148)
+#pragma unroll
+                    for (int c = 0; c < ZJ; ++c) {
+                        const double vp = v[c] * pr[c];
+                        pdfw[o * FZC + zl + 32 * c] += vp;
+                        Eo = fma(vp, wzv[c], Eo);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q + 1 < FTO; ++q) E[q] = E[q + 1];
+                E[FTO - 1] = Eo;
+            }
+        }
+        if constexpr (!SAMPLE) {
+            // evidence of (target, training galaxy k) over this z-chunk: four warp sums folded
+            // into one butterfly -- after the xor-16 step a lane keeps two of the four partial
+            // sums, after xor-8 one; lane 8 j ends up with the sum of target j
+            static_assert(FTO == 4, "butterfly written for 4 targets per warp");
+            const bool hi16 = lane & 16, hi8 = lane & 8;
+            const double s0 = hi16 ? E[0] : E[2], s1 = hi16 ? E[1] : E[3];      // what I give away
+            double k0 = hi16 ? E[2] : E[0], k1 = hi16 ? E[3] : E[1];            // what I keep
+            k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+            k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+            double ev = (hi8 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, hi8 ? k0 : k1, 8);
+            ev += __shfl_xor_sync(0xffffffffu, ev, 4);
+            ev += __shfl_xor_sync(0xffffffffu, ev, 2);
+            ev += __shfl_xor_sync(0xffffffffu, ev, 1);
+            if ((lane & 7) == 0) E_sm[(size_t)(tfirst + (lane >> 3)) * TTs + k] += ev;
+#pragma unroll
+            for (int o = 0; o < FTO; ++o) E[o] = 0.0;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[cs]);
+        if (++cs == STG) { cs = 0; cph ^= 1; }
+        if (++k == tcount) {
+            if constexpr (!SAMPLE) {
+                // end of a z-chunk: add the warp's PDF slices to the global accumulators
+#pragma unroll
+                for (int o = 0; o < FTO; ++o) {
+                    const int og = og0 + o;
+                    if (og < p.nO) {
+                        double* dst = p.pdf_acc + (size_t)og * p.nzp + z0;
+#pragma unroll
+                        for (int zj = 0; zj < FZT; ++zj) {
+                            const double a = pdfw[o * FZC + zj * 32 + lane];
+                            if (a != 0.0) atomicAdd(dst + zj * 32 + lane, a);
+                            pdfw[o * FZC + zj * 32 + lane] = 0.0;
+                        }
+                    }
+                }
+            }
+            k = 0; ++chunk;
+        }
+    }
+
+    // ---------------------------------------------------------------------- unit epilogue
+    __syncwarp();
+    if constexpr (SAMPLE) {
+#pragma unroll
+        for (int o = 0; o < FTO; ++o) {
+            const double mx = warp_max(E[o]);
+            const int og = og0 + o;
+            if (lane == 0 && og < p.nO && mx == mx) {
+                unsigned long long b = (unsigned long long)__double_as_longlong(mx);
+                b = (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+                atomicMax(p.Akey + og, b);
+            }
+        }
+    } else {
+        const int wovf = __reduce_max_sync(0xffffffffu, ovf);
+        const bool over = wovf >= HI_OVERFLOW;
+#pragma unroll
+        for (int o = 0; o < FTO; ++o) {
+            const int og = og0 + o;
+            if (og >= p.nO) continue;
+            if (p.rescue && p.flag[og] == 0) continue;         // warp-uniform
+            if (p.evid != nullptr) {
+                double* dst = p.evid + (size_t)og * p.nT + ts0;
+                for (int q = lane; q < tcount; q += 32)
+                    dst[q] = E_sm[(size_t)(tfirst + o) * TTs + q];
+            }
+            if (lane == 0) {
+                atomicMax(p.Vbits + og, V_sm[tfirst + o]);
+                if (over && !p.rescue) { p.flag[og] = 1; *p.nflag = 1; }
+            }
+        }
+    }
+}
+
+template <int NF, bool ZDEP, bool HET, int MODE>
+static int launch_fused_t(const FusedParams& p, cudaStream_t stream, bool timed) {
+    constexpr int CFG = cfg_of(NF, HET);
+    const int nU = HET ? p.nU : NF;
+    const size_t smem = fused_smem_bytes(CFG, NF, HET, ZDEP, nU, p.stages, p.TT);
+    auto kern = fused_like_kernel<NF, ZDEP, HET, MODE>;
+    DL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+    dim3 grid((unsigned)(p.nTiles * p.nTB));
+    if (timed && dl_timing_enabled()) dl_timing_mark(stream, 0);
+    kern<<<grid, cfg_warps(CFG) * 32, smem, stream>>>(p);
+    if (timed && dl_timing_enabled()) dl_timing_mark(stream, 1);
+    DL_CUDA_CHECK(cudaGetLastError());
+    dl_count_launch();
+    return DL_OK;
+}
+
+template <int NF>
+static int launch_fused_nf(bool zdep, bool het, int mode, const FusedParams& p,
+                           cudaStream_t stream, bool timed) {
+    if (het) {
+        if (zdep) {
+            dl_set_error("per-target band lists with z-dependent ell priors: group by band set");
+            return DL_ERR_UNSUPPORTED;
+        }
+        return mode == MODE_SAMPLE ? launch_fused_t<NF, false, true, MODE_SAMPLE>(p, stream, timed)
+                                   : launch_fused_t<NF, false, true, MODE_MAIN>(p, stream, timed);
+    }
+    if (zdep)
+        return mode == MODE_SAMPLE ? launch_fused_t<NF, true, false, MODE_SAMPLE>(p, stream, timed)
+                                   : launch_fused_t<NF, true, false, MODE_MAIN>(p, stream, timed);
+    return mode == MODE_SAMPLE ? launch_fused_t<NF, false, false, MODE_SAMPLE>(p, stream, timed)
+                               : launch_fused_t<NF, false, false, MODE_MAIN>(p, stream, timed);
+}
+
+}  // namespace dl

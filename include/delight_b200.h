@@ -119,11 +119,13 @@ int dl_kernel_grids_dev(long long nB, long long nzg, long long NC, long long NL,
 /* Model-grid layout of the fused likelihood: [nT][2*nB][nzp], rows 0..nB-1 = band means,
  * nB..2nB-1 = band variances, z contiguous, nzp = dl_fused_padded_nz(nz) (padding: mean 0,
  * variance 0).  Priors are [nT][nzp] (padding 0). */
-int dl_fused_chunk(void);
-int dl_fused_targets_per_cta(void);
-int dl_fused_ctas_per_sm(int nf, int zdep);   /* resident CTAs per SM for nf bands (launch sizing) */
+int dl_fused_chunk(void);                      /* nz is padded to a multiple of this (128) */
+int dl_fused_targets_per_cta(int nf, int per_target_bands);   /* 32 or 64 (launch sizing) */
+int dl_fused_ctas_per_sm(int nf, int per_target_bands);       /* resident CTAs per SM: 2 or 1 */
 long long dl_fused_padded_nz(long long nz);
-long long dl_fused_workspace_bytes(long long nO, long long nT, long long nz, int nsplit,
+/* scratch bytes of dl_like_fused_dev: per target 8 B x (nzp + nT) + ~1.5 KB; the nT term drops
+ * when the caller passes an evidence array or asks for no evidences (K = 0, evid = NULL) */
+long long dl_fused_workspace_bytes(long long nO, long long nT, long long nz,
                                    int evid_is_output_or_unused);
 
 /* legacy [nz][nT][nB] arrays of scripts/delight-apply.py:84-85 -> fused layout */
@@ -136,20 +138,34 @@ int dl_relayout_prior_dev(long long nz, long long nT, const double* prior_zt, do
 int dl_zprior_dev(long long nT, long long nz, const double* zgrid, const double* ztrain,
                   double sigma, double* prior_tz, void* stream);
 
+/* Template prior of scripts/templateFitting.py:79-83 in the fused layout [nt][nzp]:
+ * p(z,t) = p_t[t] z / p_z_t[t]^2 exp(-z^2 / (2 p_z_t[t]^2)); p_t, p_z_t device arrays [nt]. */
+int dl_template_prior_dev(long long nt, long long nz, const double* zgrid, const double* p_t,
+                          const double* p_z_t, double* prior_tz, void* stream);
+
 /* Fused likelihood + apply epilogue   replaces scripts/delight-apply.py:137-162 x nO targets
- * (approx_flux_likelihood_cy, like*=prior, pdf=sum_t, evid=trapz_z, top-K) for one group of
- * targets that share the band list `bands` (HOST array, nf <= 32 entries; up to 16 bands the
- * model values of a redshift group are cached in registers, beyond that re-read from the stage).
- *   obs/var [nO][nf]; ell_hat/ell_var scalars, or device vectors ell_hat_z/ell_var_z [nz]
+ * (approx_flux_likelihood_cy, like*=prior, pdf=sum_t, evid=trapz_z, top-K) for nO targets that
+ * are observed in nf bands each (nf <= 32).
+ *   union_bands  HOST array [n_union]: the band rows of the grid that are staged per step.
+ *   target_rows  NULL: every target is observed in exactly union_bands (n_union == nf) -- the
+ *                fastest form; else DEVICE int32 [nO][nf]: band f of target o is
+ *                union_bands[target_rows[o][f]] (the valid-band list of io.py:331-337 per target,
+ *                as delight-apply.py:141-142 selects model_mean[:, :, bands] per target), so a
+ *                catalogue with missing bands needs one call per band COUNT, not per band set.
+ *   obs/var [nO][nf] in the target's own band order; ell_hat/ell_var scalars, or device vectors
+ *   ell_hat_z/ell_var_z [nz] (not together with target_rows)
  *   pdf [nO][ld_pdf] out; evid [nO][nT] out or NULL; top_idx [nO][K] / top_ev [nO][K] out
  *   (K = 0: skipped).  Ties: descending evidence, equal -> larger index first.
  *   cov_scale multiplies the model variance (1.0 for delight-apply; delight-optimize.py:122
- *   passes V_C * model_covar). */
+ *   passes V_C * model_covar).
+ * Stream-ordered, no host synchronisation.  PDFs are accumulated with floating-point atomics:
+ * repeated calls agree to rounding (~1e-16 relative), not bit for bit. */
 int dl_like_fused_dev(long long nO, long long nT, long long nz, long long nB, int nf,
-                      const int* bands, const double* obs, const double* var,
+                      int n_union, const int* union_bands, const int* target_rows,
+                      const double* obs, const double* var,
                       const double* grid, const double* prior, const double* zgrid,
                       double ell_hat, double ell_var, const double* ell_hat_z,
-                      const double* ell_var_z, double cov_scale, int nsplit, int K, double* pdf,
+                      const double* ell_var_z, double cov_scale, int K, double* pdf,
                       long long ld_pdf,
                       double* evid, long long* top_idx, double* top_ev, void* workspace,
                       long long workspace_bytes, void* stream);

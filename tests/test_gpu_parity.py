@@ -239,6 +239,7 @@ def test_fused_golden_pipeline(sdss):
     res = apply.apply_fused(grid, prior, g["zgrid"], t, ell_hat=1.0,
                             ell_var=float(g["ellPriorSigma"]) ** 2, K=K, want_evid=True,
                             want_metrics=True, confidence_levels=g["confidenceLevels"])
+    assert res["fused_launches"] == np.unique(g["ta_nb"]).size      # per band count, not set
     ref = dict(pdf=g["pdfs"], evid=g["evid"], top_idx=g["top_idx"], top_ev=g["top_ev"])
     _check_fused(res, ref, K)
     # metrics: all 7 + nCL columns of computeMetrics (incl. the 200-level CIlevel scan) and the
@@ -268,27 +269,34 @@ def test_fused_templatefit_golden(golden, sdss):
     assert_close(res["pdf"], g["pdfs"], g["pdfs"].max(axis=1, keepdims=True) * 1e-290)
 
 
-@pytest.mark.parametrize("nO,nT,nz,nB,nf,zdep,nsplit", [
+@pytest.mark.parametrize("nO,nT,nz,nB,nf,zdep,tt", [
+    # tt: training galaxies per CTA (DL_FUSED_TT; None = default 64 / 32), i.e. how the training
+    # set is cut into units.  nf < nB with zdep=False: per-target band lists in ONE launch;
+    # zdep=True: one launch per band set.
     (70, 150, 300, 6, 6, False, None),
-    (33, 97, 129, 5, 3, True, 3),
-    (5, 40, 128, 8, 8, False, 1),
-    (40, 64, 751, 5, 5, False, 2),
+    (33, 97, 129, 5, 3, True, 16),
+    (5, 40, 128, 8, 8, False, 8),
+    (40, 64, 751, 5, 5, False, 24),
+    (70, 64, 300, 6, 4, False, None),        # 15 band sets of 4 out of 6, one launch
     (3, 33, 50, 4, 1, True, None),
-    (20, 60, 200, 16, 16, False, None),      # > 8 bands: single-redshift variant of the kernel
-    (9, 30, 129, 12, 11, True, 2),
-    # ring depth 3 / 2 / 2 (two CTAs per SM) and 4 (one CTA per SM): fused_stages()
+    (20, 60, 200, 16, 16, False, None),      # > 8 bands: model values read from the stage
+    (9, 30, 129, 12, 11, True, 9),
+    # ring depths and both configurations (8 warps x 128 z / 16 warps x 64 z): plan_launch()
     (12, 50, 200, 8, 8, True, None),
     (10, 45, 140, 10, 10, False, None),
-    (8, 40, 129, 13, 13, True, 1),
+    (8, 40, 129, 13, 13, True, 40),
     (6, 35, 100, 14, 14, False, None),
-    # more than 16 bands (G10-style): model values read from the stage instead of registers
+    # more than 16 bands (G10-style)
     (9, 31, 130, 28, 17, False, None),
-    (7, 25, 90, 28, 21, True, 2),
-    (5, 20, 129, 32, 32, False, 1),
+    (7, 25, 90, 28, 21, True, 12),
+    (70, 25, 90, 28, 21, False, None),
+    (5, 20, 129, 32, 32, False, 20),
     (5, 20, 129, 27, 27, True, None),
 ])
-def test_fused_vs_oracle_random(orc, nO, nT, nz, nB, nf, zdep, nsplit):
+def test_fused_vs_oracle_random(orc, monkeypatch, nO, nT, nz, nB, nf, zdep, tt):
     from delight_b200 import apply
+    if tt is not None:
+        monkeypatch.setenv("DL_FUSED_TT", str(tt))
     rng = np.random.default_rng(nO * 1000 + nT)
     zgrid = np.sort(rng.uniform(0.01, 3.0, nz)) if zdep else np.linspace(0.01, 3.0, nz)
     shape = rng.uniform(0.5, 2.0, (1, nT, nB)) * (1 + np.sin(zgrid[:, None, None] * rng.uniform(
@@ -322,8 +330,10 @@ def test_fused_vs_oracle_random(orc, nO, nT, nz, nB, nf, zdep, nsplit):
     t = apply.Targets(fl, fv, bands, nfs)
     res = apply.apply_fused(grid, dprior, zgrid, t,
                             ell_hat=ell_hat if zdep else 1.0, ell_var=ell_var if zdep else 0.25,
-                            K=K, want_evid=True, nsplit=nsplit)
+                            K=K, want_evid=True)
     _check_fused(res, ref, K)
+    # one launch per band COUNT (per band set only with z-dependent ell priors)
+    assert res["fused_launches"] == (1 if not zdep else len(list(t.groups())))
 
 
 def test_fused_topk_ties_and_underflow(orc):
@@ -365,10 +375,11 @@ def test_fused_topk_ties_and_underflow(orc):
     np.testing.assert_array_equal(res["top_idx"][nz_top], ref["top_idx"][nz_top])
 
 
-def test_fused_full_size_properties():
+def test_fused_full_size_properties(monkeypatch):
     """Size-independent properties at the bench shape (nz=1500, 6 bands): results do not depend
-    on how the training set is split across CTAs nor on target order; duplicated targets give
-    identical rows; the PDF of a noiseless target peaks at its source redshift."""
+    on how the training set is split across CTAs nor on target order (up to the rounding of the
+    PDF's floating-point atomics); duplicated targets give the same rows; the PDF of a noiseless
+    target peaks at its source redshift."""
     import torch
     from delight_b200 import apply
     rng = np.random.default_rng(5)
@@ -385,9 +396,12 @@ def test_fused_full_size_properties():
     grid = apply.ModelGrid.from_legacy(mm, mc)
     prior = grid.gaussian_prior(zgrid, zt, 0.5)
     a = apply.apply_fused(grid, prior, zgrid, apply.Targets.full(fl, fv), ell_var=0.25, K=50,
-                          nsplit=1, want_metrics=True)
-    b = apply.apply_fused(grid, prior, zgrid, apply.Targets.full(fl, fv), ell_var=0.25, K=50,
-                          nsplit=4)
+                          want_metrics=True)
+    monkeypatch.setenv("DL_FUSED_TT", "23")
+    monkeypatch.setenv("DL_FUSED_G", "2")
+    b = apply.apply_fused(grid, prior, zgrid, apply.Targets.full(fl, fv), ell_var=0.25, K=50)
+    monkeypatch.delenv("DL_FUSED_TT")
+    monkeypatch.delenv("DL_FUSED_G")
     np.testing.assert_allclose(a["pdf"], b["pdf"], rtol=1e-11, atol=1e-290)
     # evidences next to the underflow boundary may flush to zero along one path and not the
     # other (then they tie at 0): compare the ranking where the evidence is representable
@@ -397,10 +411,11 @@ def test_fused_full_size_properties():
     np.testing.assert_allclose(a["top_ev"][solid], b["top_ev"][solid], rtol=1e-11)
     perm = rng.permutation(nO)
     c = apply.apply_fused(grid, prior, zgrid, apply.Targets.full(fl[perm], fv[perm]),
-                          ell_var=0.25, K=50, nsplit=1)      # same split as `a`: bit-exact
-    np.testing.assert_array_equal(c["pdf"], a["pdf"][perm])
-    np.testing.assert_array_equal(c["top_idx"], a["top_idx"][perm])
-    np.testing.assert_array_equal(a["pdf"][0], a["pdf"][1])
+                          ell_var=0.25, K=50)
+    np.testing.assert_allclose(c["pdf"], a["pdf"][perm], rtol=1e-12, atol=1e-290)
+    np.testing.assert_array_equal(c["top_idx"][solid[perm]], a["top_idx"][perm][solid[perm]])
+    np.testing.assert_allclose(a["pdf"][0], a["pdf"][1], rtol=1e-12, atol=1e-290)
+    np.testing.assert_array_equal(a["top_ev"][0], a["top_ev"][1])   # evidences: no atomics
     assert (a["top_idx"][np.arange(nO), 0] == src).mean() > 0.9
     assert np.all(np.diff(a["top_ev"], axis=1) <= 0)
     assert np.isfinite(a["pdf"]).all() and (a["pdf"] >= 0).all()
@@ -601,7 +616,7 @@ def test_templatefit_config2_scale_properties():
                             ell_var=1e24, K=0, want_metrics=True, workspace=ws)
     assert res["fused_launches"] > 1
     small = apply.apply_fused(grid, prior, zgrid, apply.Targets.full(fl[:64], fv[:64]),
-                              ell_hat=1.0, ell_var=1e24, K=0, nsplit=1)
+                              ell_hat=1.0, ell_var=1e24, K=0)
     np.testing.assert_allclose(res["pdf"][:64], small["pdf"], rtol=1e-11, atol=1e-290)
     assert np.isfinite(res["pdf"]).all() and (res["pdf"] >= 0).all()
     # noiseless targets: the posterior mode sits on the source redshift unless the p(z,t) prior

@@ -31,11 +31,17 @@ def test_library_exports_every_declared_symbol():
 def test_padding_and_workspace_queries():
     L = _lib.lib()
     c = L.dl_fused_chunk()
-    assert c == 128 and L.dl_fused_targets_per_cta() in (31, 32)
+    assert c == 128
+    assert L.dl_fused_targets_per_cta(6, 0) == 32 and L.dl_fused_ctas_per_sm(6, 0) == 2
+    assert L.dl_fused_targets_per_cta(6, 1) == 64 and L.dl_fused_ctas_per_sm(21, 0) == 1
     assert L.dl_fused_padded_nz(1500) == 1536 and L.dl_fused_padded_nz(128) == 128
-    a = L.dl_fused_workspace_bytes(31, 1000, 1500, 1, 0)
-    b = L.dl_fused_workspace_bytes(62, 1000, 1500, 1, 0)
+    a = L.dl_fused_workspace_bytes(32, 1000, 1500, 0)
+    b = L.dl_fused_workspace_bytes(64, 1000, 1500, 0)
     assert 0 < a < b
+    # the raw evidences (8 B per target x training galaxy) dominate: no per-z-chunk partials
+    big = L.dl_fused_workspace_bytes(1000, 100000, 1500, 0)
+    assert big < 1000 * (8 * 100000 + 8 * 1536 + 4096)
+    assert L.dl_fused_workspace_bytes(1000, 100000, 1500, 1) < 1000 * (8 * 1536 + 4096)
 
 
 def test_rank_partition_matches_reference_formula():

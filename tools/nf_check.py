@@ -23,7 +23,7 @@ for nf in [int(a) for a in sys.argv[1:]]:
     ref = orc.apply_fused(fl, fv, nfs, bands, mm, mc, prior, zgrid, np.ones(nz), np.full(nz, 0.25), 10, want_evid=True)
     grid = apply.ModelGrid.from_legacy(mm, mc)
     res = apply.apply_fused(grid, grid.gaussian_prior(zgrid, zt, 0.5), zgrid, apply.Targets(fl, fv, bands, nfs),
-                            ell_hat=1.0, ell_var=0.25, K=10, want_evid=True, nsplit=1)
+                            ell_hat=1.0, ell_var=0.25, K=10, want_evid=True)
     bad = ~np.isfinite(res["pdf"])
     rel = np.abs(res["pdf"] / np.where(ref["pdf"] > 1e-250 * ref["pdf"].max(axis=1, keepdims=True), ref["pdf"], np.nan) - 1)
     ebad = ~np.isfinite(res["evid"])

@@ -1,6 +1,7 @@
 """Fused-kernel time vs number of bands (synthetic grid, kernel events via dl_timing_*):
 python tools/nf_scan.py [nO nT]"""
 import ctypes
+import os
 import sys
 
 import numpy as np
@@ -12,7 +13,7 @@ nO, nT = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (2048, 1
 nz = 1500
 L = _lib.lib()
 zgrid = np.linspace(0.01, 3.0, nz)
-for nf in (9, 10, 12, 13, 14, 16, 21, 28):
+for nf in [int(x) for x in os.environ.get('NF_LIST', '4,6,8,9,10,13,16,21,28').split(',')]:
     g = torch.Generator(device="cuda").manual_seed(nf)
     mean = 1e5 * (0.5 + torch.rand((nz, nT, nf), generator=g, device="cuda", dtype=torch.float64))
     var = (mean * 0.01) ** 2
