@@ -48,6 +48,9 @@ constexpr int ZJ = 2;         // redshifts a lane processes jointly (independent
 #ifndef DL_PREF
 #define DL_PREF 2
 #endif
+#ifndef DL_TJ2_NF
+#define DL_TJ2_NF 17
+#endif
 #ifndef DL_CFG1_NF
 #define DL_CFG1_NF 9          // homogeneous band sets from here on use config 1
 #endif
@@ -129,89 +132,125 @@ struct SmemModelHet {
     __device__ __forceinline__ double cv(int c, int f) const { return stz[off[f] + var0 + 32 * c]; }
 };
 
-template <int NF, class Model>
-__device__ __forceinline__ void cells_xy(const double* tc, const Model md, const double (&pOT0)[ZJ],
-                                         const double (&pOT)[ZJ], const double (&pTT)[ZJ],
-                                         const double (&pOO)[ZJ], const double (&zev)[ZJ],
-                                         const double (&xmask)[ZJ], double (&x)[ZJ],
-                                         double (&y)[ZJ]) {
-    const double2* tc0 = reinterpret_cast<const double2*>(tc);             // (a s, w)
-    const double2* tc1 = reinterpret_cast<const double2*>(tc + 2 * NF);    // (var', obs)
-    const double* tc2 = tc + 4 * NF;                                       // obs^2
-    const double hc = tc[5 * NF + TC_HC];
-    // pass 0: observed variances only (utils_cy.pyx:101-113 with ellML = 0)
-    double fot[ZJ], ftt[ZJ], foo[ZJ], P[ZJ], P2[ZJ], e2[ZJ];   // det = P * P2 (P2 only for NF > REGNF)
+// TJ targets are evaluated jointly against the same ZJ cells: every model value is read once
+// for all of them (with the model in shared memory that halves the dominant LDS traffic) and
+// every statement carries TJ x ZJ independent dependency chains.
+template <int NF, int TJ, class Model>
+__device__ __forceinline__ void cells_xy(const double* const (&tcs)[TJ], const Model md,
+                                         const double (&pOT0)[TJ][ZJ], const double (&pOT)[TJ][ZJ],
+                                         const double (&pTT)[TJ][ZJ], const double (&pOO)[TJ][ZJ],
+                                         const double (&zev)[ZJ], const double (&xmask)[TJ][ZJ],
+                                         double (&x)[TJ][ZJ], double (&y)[TJ][ZJ]) {
+    const double2* tc0[TJ];     // (a s, w)
+    const double2* tc1[TJ];     // (var', obs)
+    const double* tc2[TJ];      // obs^2
 #pragma unroll
-    for (int c = 0; c < ZJ; ++c) { fot[c] = pOT0[c]; ftt[c] = pTT[c]; }
+    for (int j = 0; j < TJ; ++j) {
+        tc0[j] = reinterpret_cast<const double2*>(tcs[j]);
+        tc1[j] = reinterpret_cast<const double2*>(tcs[j] + 2 * NF);
+        tc2[j] = tcs[j] + 4 * NF;
+    }
+    // pass 0: observed variances only (utils_cy.pyx:101-113 with ellML = 0)
+    double fot[TJ][ZJ], ftt[TJ][ZJ], foo[TJ][ZJ], P[TJ][ZJ], P2[TJ][ZJ], e2[TJ][ZJ];
+#pragma unroll
+    for (int j = 0; j < TJ; ++j)
+#pragma unroll
+        for (int c = 0; c < ZJ; ++c) { fot[j][c] = pOT0[j][c]; ftt[j][c] = pTT[j][c]; }
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
-        const double2 aw = tc0[f];
+        double mf[ZJ];
 #pragma unroll
-        for (int c = 0; c < ZJ; ++c) {
-            const double mf = md.m(c, f);
-            const double tw = mf * aw.y;
-            fot[c] = fma(mf, aw.x, fot[c]);
-            ftt[c] = fma(tw, mf, ftt[c]);
+        for (int c = 0; c < ZJ; ++c) mf[c] = md.m(c, f);
+#pragma unroll
+        for (int j = 0; j < TJ; ++j) {
+            const double2 aw = tc0[j][f];
+#pragma unroll
+            for (int c = 0; c < ZJ; ++c) {
+                const double tw = mf[c] * aw.y;
+                fot[j][c] = fma(mf[c], aw.x, fot[j][c]);
+                ftt[j][c] = fma(tw, mf[c], ftt[j][c]);
+            }
         }
     }
 #pragma unroll
-    for (int c = 0; c < ZJ; ++c) {
-        const double ell = fot[c] * rcp_fast(ftt[c]);     // ellML * sqrt(cov_scale / c)
-        e2[c] = ell * ell;
-        fot[c] = pOT[c]; ftt[c] = pTT[c]; foo[c] = pOO[c]; P[c] = zev[c]; P2[c] = 1.0;
-    }
+    for (int j = 0; j < TJ; ++j)
+#pragma unroll
+        for (int c = 0; c < ZJ; ++c) {
+            const double ell = fot[j][c] * rcp_fast(ftt[j][c]);     // ellML * sqrt(cov_scale / c)
+            e2[j][c] = ell * ell;
+            fot[j][c] = pOT[j][c]; ftt[j][c] = pTT[j][c]; foo[j][c] = pOO[j][c];
+            P[j][c] = zev[c]; P2[j][c] = 1.0;
+        }
     // pass 1: variance inflated by ell^2 * model variance (utils_cy.pyx:107-112).  Bands in
     // pairs: ONE reciprocal of the product of the pair's variances gives both 1/var
     // (r_a = var_b / (var_a var_b)) and the pair's factor of the determinant: 9 FP64
     // instructions + 1 MUFU per pair instead of 10 + 2.
-    auto acc = [&](int c, int f, double r, double ob) {
-        const double mf = md.m(c, f);
+    auto acc = [&](int j, int c, int f, double mf, double r, double ob) {
         const double tm = mf * r;
-        fot[c] = fma(tm, ob, fot[c]);
-        ftt[c] = fma(tm, mf, ftt[c]);
-        foo[c] = fma(tc2[f], r, foo[c]);
+        fot[j][c] = fma(tm, ob, fot[j][c]);
+        ftt[j][c] = fma(tm, mf, ftt[j][c]);
+        foo[j][c] = fma(tc2[j][f], r, foo[j][c]);
     };
     constexpr int NG = (NF / 2) * 2;
 #pragma unroll
     for (int f = 0; f < NG; f += 2) {
-        const double2 voa = tc1[f], vob = tc1[f + 1];
+        double ma[ZJ], mb[ZJ], ca[ZJ], cb[ZJ];
 #pragma unroll
         for (int c = 0; c < ZJ; ++c) {
-            const double va = fma(e2[c], md.cv(c, f), voa.x);
-            const double vb = fma(e2[c], md.cv(c, f + 1), vob.x);
-            const double pab = va * vb;
-            const double ri = rcp_fast(pab);
-            acc(c, f, vb * ri, voa.y);
-            acc(c, f + 1, va * ri, vob.y);
-            if (NF > REGNF && f >= NF / 2) P2[c] *= pab; else P[c] *= pab;
+            ma[c] = md.m(c, f); mb[c] = md.m(c, f + 1);
+            ca[c] = md.cv(c, f); cb[c] = md.cv(c, f + 1);
+        }
+#pragma unroll
+        for (int j = 0; j < TJ; ++j) {
+            const double2 voa = tc1[j][f], vob = tc1[j][f + 1];
+#pragma unroll
+            for (int c = 0; c < ZJ; ++c) {
+                const double va = fma(e2[j][c], ca[c], voa.x);
+                const double vb = fma(e2[j][c], cb[c], vob.x);
+                const double pab = va * vb;
+                const double ri = rcp_fast(pab);
+                acc(j, c, f, ma[c], vb * ri, voa.y);
+                acc(j, c, f + 1, mb[c], va * ri, vob.y);
+                if (NF > REGNF && f >= NF / 2) P2[j][c] *= pab; else P[j][c] *= pab;
+            }
         }
     }
     if (NF - NG == 1) {
         constexpr int f = NF - 1;
-        const double2 vo = tc1[f];
+        double ma[ZJ], ca[ZJ];
 #pragma unroll
-        for (int c = 0; c < ZJ; ++c) {
-            const double var = fma(e2[c], md.cv(c, f), vo.x);
-            acc(c, f, rcp_fast(var), vo.y);
-            if (NF > REGNF) P2[c] *= var; else P[c] *= var;
+        for (int c = 0; c < ZJ; ++c) { ma[c] = md.m(c, f); ca[c] = md.cv(c, f); }
+#pragma unroll
+        for (int j = 0; j < TJ; ++j) {
+            const double2 vo = tc1[j][f];
+#pragma unroll
+            for (int c = 0; c < ZJ; ++c) {
+                const double var = fma(e2[j][c], ca[c], vo.x);
+                acc(j, c, f, ma[c], rcp_fast(var), vo.y);
+                if (NF > REGNF) P2[j][c] *= var; else P[j][c] *= var;
+            }
         }
     }
     // chi2 and (det)^-1/2 (utils_cy.pyx:111-118)
 #pragma unroll
-    for (int c = 0; c < ZJ; ++c) {
-        double rF;
-        if (NF > REGNF) {
-            // many bands: the determinant is kept as two factors so that it cannot leave the
-            // double range (model variance >> observed variance in every band), and 1/FTT has
-            // its own reciprocal
-            y[c] = rsqrt_fast(P[c] * ftt[c]) * rsqrt_fast(P2[c]);
-            rF = rcp_fast(ftt[c]);
-        } else {
-            y[c] = rsqrt_fast(P[c] * ftt[c]);
-            rF = (y[c] * y[c]) * P[c];               // 1 / FTT
+    for (int j = 0; j < TJ; ++j) {
+        const double hc = tcs[j][5 * NF + TC_HC];
+#pragma unroll
+        for (int c = 0; c < ZJ; ++c) {
+            double rF;
+            if (NF > REGNF) {
+                // many bands: the determinant is kept as two factors so that it cannot leave
+                // the double range (model variance >> observed variance in every band), and
+                // 1/FTT has its own reciprocal
+                y[j][c] = rsqrt_fast(P[j][c] * ftt[j][c]) * rsqrt_fast(P2[j][c]);
+                rF = rcp_fast(ftt[j][c]);
+            } else {
+                y[j][c] = rsqrt_fast(P[j][c] * ftt[j][c]);
+                rF = (y[j][c] * y[j][c]) * P[j][c];               // 1 / FTT
+            }
+            const double chi2 = fma(-(fot[j][c] * rF), fot[j][c], foo[j][c]);
+            x[j][c] = fma(hc, chi2, xmask[j][c]);     // -chi2/2 - A in the target's units
         }
-        const double chi2 = fma(-(fot[c] * rF), fot[c], foo[c]);
-        x[c] = fma(hc, chi2, xmask[c]);              // -chi2/2 - A in the target's units
     }
 }
 
@@ -227,6 +266,11 @@ fused_like_kernel(const FusedParams p) {
     constexpr int TCS = tc_stride(NF, HET);
     constexpr bool SMODEL = HET || NF > REGNF;        // model values stay in the stage
     constexpr bool SAMPLE = MODE == MODE_SAMPLE;
+    // targets evaluated jointly: two from DL_TJ2_NF bands on, where the model values are read from
+    // the stage for every use and sharing them pays (measured, 2048 x 1500 x 1500 cells, one vs
+    // two targets: 13 bands 77.3 / 79.9 ms, 16: 92.5 / 98.3, 21: 131.6 / 126.5, 28: 178.5 / 173.1)
+    constexpr int TJ = (SMODEL && !HET && NF >= DL_TJ2_NF) ? 2 : 1;
+    static_assert(FTO % TJ == 0, "TJ must divide the targets of a warp");
     const int nU = HET ? p.nU : NF;
     const int ROWS = 2 * nU + 2 + (ZDEP ? 4 : 0);
     const int STG = p.stages;
@@ -406,73 +450,85 @@ fused_like_kernel(const FusedParams p) {
                 }
             }
 #pragma unroll (SMODEL || SAMPLE ? 1 : FTO)
-            for (int o = 0; o < FTO; ++o) {
-                // E[] is rotated once per target so the loop can stay rolled with the
-                // accumulators in registers (FTO rotations restore the order)
-                double Eo = E[0];
-                const double* tc = tcw + o * TCS;
-                const double* tk = tc + 5 * NF;
-                double pOT0[ZJ], pOT[ZJ], pTT[ZJ], pOO[ZJ], xm[ZJ];
+            for (int o = 0; o < FTO; o += TJ) {
+                // E[] is rotated once per target (group) so the loop can stay rolled with the
+                // accumulators in registers (FTO / TJ rotations restore the order)
+                double Eo[TJ];
+                const double* tcs[TJ];
+                double pOT0[TJ][ZJ], pOT[TJ][ZJ], pTT[TJ][ZJ], pOO[TJ][ZJ], xm[TJ][ZJ];
 #pragma unroll
-                for (int c = 0; c < ZJ; ++c) {
-                    if (ZDEP) {
-                        const double cc = tk[TC_C];
-                        pOT0[c] = tk[TC_CS] * zot[c];
-                        pOT[c] = cc * zot[c]; pTT[c] = cc * ztt[c]; pOO[c] = cc * zoo[c];
-                        xm[c] = SAMPLE ? xmask[c] : xmask[c] + tk[TC_XOFF];     // -A
-                    } else {
-                        // the anchor is folded into the constant term of FOO (TC_POO); the
-                        // sampling pass measures the un-anchored exponent (TC_POO0)
-                        pOT0[c] = tk[TC_POT0];
-                        pOT[c] = tk[TC_POT]; pTT[c] = tk[TC_PTT];
-                        pOO[c] = tk[SAMPLE ? TC_POO0 : TC_POO];
-                        xm[c] = xmask[c];
+                for (int j = 0; j < TJ; ++j) {
+                    Eo[j] = E[j];
+                    tcs[j] = tcw + (o + j) * TCS;
+                    const double* tk = tcs[j] + 5 * NF;
+#pragma unroll
+                    for (int c = 0; c < ZJ; ++c) {
+                        if (ZDEP) {
+                            const double cc = tk[TC_C];
+                            pOT0[j][c] = tk[TC_CS] * zot[c];
+                            pOT[j][c] = cc * zot[c]; pTT[j][c] = cc * ztt[c];
+                            pOO[j][c] = cc * zoo[c];
+                            xm[j][c] = SAMPLE ? xmask[c] : xmask[c] + tk[TC_XOFF];     // -A
+                        } else {
+                            // the anchor is folded into the constant term of FOO (TC_POO); the
+                            // sampling pass measures the un-anchored exponent (TC_POO0)
+                            pOT0[j][c] = tk[TC_POT0];
+                            pOT[j][c] = tk[TC_POT]; pTT[j][c] = tk[TC_PTT];
+                            pOO[j][c] = tk[SAMPLE ? TC_POO0 : TC_POO];
+                            xm[j][c] = xmask[c];
+                        }
                     }
                 }
-                double x[ZJ], y[ZJ];
+                double x[TJ][ZJ], y[TJ][ZJ];
                 if constexpr (HET)
-                    cells_xy<NF>(tc, SmemModelHet<NF, FZC>{st + zl,
-                                     reinterpret_cast<const int*>(tk + TC_NCONST), var0},
-                                 pOT0, pOT, pTT, pOO, zev, xm, x, y);
+                    cells_xy<NF, TJ>(tcs, SmemModelHet<NF, FZC>{st + zl,
+                                         reinterpret_cast<const int*>(tcs[0] + 5 * NF + TC_NCONST),
+                                         var0},
+                                     pOT0, pOT, pTT, pOO, zev, xm, x, y);
                 else if constexpr (SMODEL)
-                    cells_xy<NF>(tc, SmemModel<NF, FZC>{st + zl}, pOT0, pOT, pTT, pOO, zev, xm, x, y);
+                    cells_xy<NF, TJ>(tcs, SmemModel<NF, FZC>{st + zl}, pOT0, pOT, pTT, pOO, zev,
+                                     xm, x, y);
                 else
-                    cells_xy<NF>(tc, RegModel<NF>{m, cv}, pOT0, pOT, pTT, pOO, zev, xm, x, y);
-                if constexpr (SAMPLE) {
-                    double xl = x[0];
+                    cells_xy<NF, TJ>(tcs, RegModel<NF>{m, cv}, pOT0, pOT, pTT, pOO, zev, xm, x, y);
 #pragma unroll
-                    for (int c = 1; c < ZJ; ++c) xl = fmax(xl, x[c]);
-                    Eo = fmax(Eo, xl);
-                } else {
-                    double v[ZJ];
-                    int vh = 0;
+                for (int j = 0; j < TJ; ++j) {
+                    if constexpr (SAMPLE) {
+                        double xl = x[j][0];
 #pragma unroll
-                    for (int c = 0; c < ZJ; ++c) {
-                        v[c] = exp_nonpos_tab(x[c], etab) * y[c];          // :118,128
-                        ovf = max(ovf, __double2hiint(x[c]));
-                        vh = max(vh, __double2hiint(v[c]));
-                    }
-                    // running max of v (the final divisor), kept per target in shared memory:
-                    // only the high word is read here; the rare record-breaking cells take the
-                    // slow path (O(log) times per lane)
-                    if (vh >= reinterpret_cast<const int*>(V_sm + tfirst + o)[1]) {
+                        for (int c = 1; c < ZJ; ++c) xl = fmax(xl, x[j][c]);
+                        Eo[j] = fmax(Eo[j], xl);
+                    } else {
+                        double v[ZJ];
+                        int vh = 0;
 #pragma unroll
-                        for (int c = 0; c < ZJ; ++c)
-                            if (v[c] == v[c])
-                                atomicMax(V_sm + tfirst + o,
-                                          (unsigned long long)__double_as_longlong(v[c]));
-                    }
-                    // prior, PDF and evidence accumulation  (delight-apply.py:145-148)
+                        for (int c = 0; c < ZJ; ++c) {
+                            v[c] = exp_nonpos_tab(x[j][c], etab) * y[j][c];      // :118,128
+                            ovf = max(ovf, __double2hiint(x[j][c]));
+                            vh = max(vh, __double2hiint(v[c]));
+                        }
+                        // running max of v (the final divisor), kept per target in shared
+                        // memory: only the high word is read here; the rare record-breaking
+                        // cells take the slow path (O(log) times per lane)
+                        unsigned long long* Vt = V_sm + tfirst + o + j;
+                        if (vh >= reinterpret_cast<const int*>(Vt)[1]) {
 #pragma unroll
-                    for (int c = 0; c < ZJ; ++c) {
-                        const double vp = v[c] * pr[c];
-                        pdfw[o * FZC + zl + 32 * c] += vp;
-                        Eo = fma(vp, wzv[c], Eo);
+                            for (int c = 0; c < ZJ; ++c)
+                                if (v[c] == v[c])
+                                    atomicMax(Vt, (unsigned long long)__double_as_longlong(v[c]));
+                        }
+                        // prior, PDF and evidence accumulation  (delight-apply.py:145-148)
+#pragma unroll
+                        for (int c = 0; c < ZJ; ++c) {
+                            const double vp = v[c] * pr[c];
+                            pdfw[(o + j) * FZC + zl + 32 * c] += vp;
+                            Eo[j] = fma(vp, wzv[c], Eo[j]);
+                        }
                     }
                 }
 #pragma unroll
-                for (int q = 0; q + 1 < FTO; ++q) E[q] = E[q + 1];
-                E[FTO - 1] = Eo;
+                for (int q = 0; q + TJ < FTO; ++q) E[q] = E[q + TJ];
+#pragma unroll
+                for (int j = 0; j < TJ; ++j) E[FTO - TJ + j] = Eo[j];
             }
         }
         if constexpr (!SAMPLE) {

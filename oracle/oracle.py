@@ -392,3 +392,103 @@ def ci_level(redshiftGrid, pdf, fraction, numlevels=200):
         if trapz(pdf[ind], redshiftGrid[ind]) >= fraction * ev:
             return level
     return None
+
+
+def gp_predict_interp_hp(grids, V_C, V_L, tmpl_table, zfine, redshiftGridGP, bands, z, ell,
+                         bestType, L, D, redshiftGrid):
+    """Higher-precision truth for gp_predict_interp: the same formulas (photoz_gp.py:236-347,
+    SURVEY Appendix C) on the same float64 inputs, every operation in np.longdouble (x86: 64-bit
+    mantissa, eps 1.1e-19) with explicit substitutions instead of LAPACK.  The model variance
+    `Kdiag - k^T A^-1 k` cancels ~8 digits, so float64 implementations (the reference's
+    cho_solve + dot, the GPU's |L^-1 k|^2) sit 1e-9..1e-7 away from this value and from each
+    other; tests/test_oracle.py and tests/test_gpu_parity.py measure both distances."""
+    ld = np.longdouble
+    nB = grids["KC"].shape[0]
+    zg = np.asarray(redshiftGridGP, dtype=float)
+    nzg = len(zg)
+    bands = np.asarray(bands, dtype=np.int64)
+    B = len(bands)
+    fz = grids["fzGrid"].astype(ld)
+    KC, KL = grids["KC"], grids["KL"]
+
+    def zeta_hp(zz):
+        zz = ld(zz)
+        dl = np.exp(ld(30.5) * np.power(zz, ld(0.04)) - ld(21.7))
+        return (ld(1) + zz) / (np.sqrt(ld(4) * ld(np.pi) * ld(1.0)) * dl)
+
+    def findpos(x):
+        x = float(x)
+        g = grids["fzGrid"]
+        if not (x >= g[0] and x <= g[-1]):
+            return 0
+        for p in range(len(g) - 1):
+            if g[p] <= x <= g[p + 1]:
+                return p
+        return 0
+
+    def bilin(G, p1, x, p2, y):
+        xl, xh, yl, yh = fz[p1], fz[p1 + 1], fz[p2], fz[p2 + 1]
+        x, y = ld(x), ld(y)
+        inv = ld(1) / (xh - xl) / (yh - yl)
+        return inv * ((xh - x) * (yh - y) * ld(G[p1, p2]) + (x - xl) * (yh - y) * ld(G[p1 + 1, p2])
+                      + (xh - x) * (y - yl) * ld(G[p1, p2 + 1])
+                      + (x - xl) * (y - yl) * ld(G[p1 + 1, p2 + 1]))
+
+    Lh = np.asarray(L, dtype=float).astype(ld)
+    Dh = np.asarray(D, dtype=float).astype(ld)
+
+    def fwd(b):
+        w = np.zeros(B, dtype=ld)
+        for j in range(B):
+            s = b[j]
+            for m in range(j):
+                s = s - Lh[j, m] * w[m]
+            w[j] = s / Lh[j, j]
+        return w
+
+    def bwd(w):
+        x = np.zeros(B, dtype=ld)
+        for j in range(B - 1, -1, -1):
+            s = w[j]
+            for m in range(j + 1, B):
+                s = s - Lh[m, j] * x[m]
+            x[j] = s / Lh[j, j]
+        return x
+
+    beta = bwd(fwd(Dh))
+    ellh = ld(ell)
+    zz = zeta_hp(z)
+    x = 1.0 + z
+    p2 = findpos(x)
+    mean = np.zeros((nB, nzg), dtype=ld)
+    var = np.zeros((nB, nzg), dtype=ld)
+    VC, VL = ld(V_C), ld(V_L)
+    for bs in range(nB):
+        for iz in range(nzg):
+            xs = 1.0 + zg[iz]
+            p1 = findpos(xs)
+            zs = zeta_hp(zg[iz])
+            pref = zs * zs * zz * zz * ellh * ellh
+            k = np.zeros(B, dtype=ld)
+            for j in range(B):
+                bj = int(bands[j])
+                k[j] = pref * (VC * bilin(KC[bs, bj], p1, xs, p2, x)
+                               + VL * bilin(KL[bs, bj], p1, xs, p2, x))
+            v = bwd(fwd(k))
+            kd = zs ** 4 * ellh * ellh * (VC * ld(grids["KCd"][bs, iz]) + VL * ld(grids["KLd"][bs, iz]))
+            var[bs, iz] = kd - np.dot(k, v)
+            tab = tmpl_table[bestType, bs]
+            zf = np.asarray(zfine, dtype=float)
+            i = int(np.clip(np.searchsorted(zf, zg[iz]), 1, len(zf) - 1) - 1)
+            slope = (ld(tab[i + 1]) - ld(tab[i])) / (ld(zf[i + 1]) - ld(zf[i]))
+            mean[bs, iz] = np.dot(k, beta) + ellh * (slope * (ld(zg[iz]) - ld(zf[i])) + ld(tab[i]))
+    rg = np.asarray(redshiftGrid, dtype=float)
+    ii = np.clip(np.searchsorted(zg, rg), 1, nzg - 1) - 1
+    zgl, rgl = zg.astype(ld), rg.astype(ld)
+    model_mean = np.zeros((len(rg), nB), dtype=ld)
+    model_var = np.zeros_like(model_mean)
+    for b in range(nB):
+        for arr, out in ((mean, model_mean), (var, model_var)):
+            slope = (arr[b, ii + 1] - arr[b, ii]) / (zgl[ii + 1] - zgl[ii])
+            out[:, b] = slope * (rgl - zgl[ii]) + arr[b, ii]
+    return model_mean, model_var
