@@ -58,6 +58,8 @@ _SIGS = {
                       c_p, c_p, c_p, c_p, c_p, c_ll, c_p],
     "dl_gp_predict_dev": [c_ll, c_ll, c_ll, c_ll, c_ll, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
                           c_d, c_d, c_p, c_ll, c_p, c_p, c_p],
+    "dl_gp_predict_at_dev": [c_ll, c_ll, c_ll, c_ll, c_ll, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
+                             c_d, c_d, c_p, c_ll, c_p, c_p, c_p],
     "dl_launch_count": [],
     "dl_timing_enable": [c_i],
     "dl_timing_collect": [c_p, c_p],

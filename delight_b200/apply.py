@@ -163,6 +163,19 @@ class ModelGrid:
                                            float(sigma), _lib.ptr(prior), _lib.stream_ptr()))
         return prior
 
+    def template_prior(self, zgrid, p_t, p_z_t):
+        """p(z, t) = p_t z / p_z_t^2 exp(-z^2 / (2 p_z_t^2))  (scripts/templateFitting.py:79-83)
+        for a grid whose nT "training galaxies" are the nt templates -> [nt][nzp]."""
+        torch = _lib.require_cuda()
+        zg, pt, pzt = _as_dev(zgrid), _as_dev(p_t), _as_dev(p_z_t)
+        if zg.numel() != self.nz or pt.numel() != self.nT or pzt.numel() != self.nT:
+            raise ValueError("template_prior: zgrid [nz], p_t [nt], p_z_t [nt]")
+        prior = torch.empty((self.nT, self.nzp), dtype=torch.float64, device="cuda")
+        _lib.check(_lib.lib().dl_template_prior_dev(self.nT, self.nz, _lib.ptr(zg), _lib.ptr(pt),
+                                                   _lib.ptr(pzt), _lib.ptr(prior),
+                                                   _lib.stream_ptr()))
+        return prior
+
     def explicit_prior(self, prior_zt):
         """From an explicit prior[nz, nT] (e.g. scripts/templateFitting.py:79-82)."""
         torch = _lib.require_cuda()

@@ -182,7 +182,8 @@ constexpr int PRED_THREADS = 128;
 
 __global__ void __launch_bounds__(PRED_THREADS) gp_predict_kernel(
     GPModel gm, int nT, const double* __restrict__ rows, int numCol, int nzp,
-    double* __restrict__ grid, double* __restrict__ train_z) {
+    double* __restrict__ grid, double* __restrict__ train_z, const double* __restrict__ zeval,
+    double* __restrict__ at_out) {
     extern __shared__ double sm[];
     const int nB = gm.nB, nzg = gm.nzg, nt = gm.nt, nz = gm.nz;
     double* L = sm;                                   // [32][33]
@@ -210,10 +211,14 @@ __global__ void __launch_bounds__(PRED_THREADS) gp_predict_kernel(
     __syncthreads();
     const int B = s_B;
     const double z = s_z, ell = s_ell;
-    double* g_mean = grid + (size_t)gi * 2 * nB * nzp;
-    double* g_var = g_mean + (size_t)nB * nzp;
+    double* g_mean = grid ? grid + (size_t)gi * 2 * nB * nzp : nullptr;
+    double* g_var = grid ? g_mean + (size_t)nB * nzp : nullptr;
     if (B < 1 || B > GP_MAXB) {           // invalid core: neutral rows
-        for (int i = tid; i < nB * nzp; i += PRED_THREADS) { g_mean[i] = 0.0; g_var[i] = 1.0; }
+        if (grid)
+            for (int i = tid; i < nB * nzp; i += PRED_THREADS) { g_mean[i] = 0.0; g_var[i] = 1.0; }
+        if (at_out)
+            for (int i = tid; i < 2 * nB; i += PRED_THREADS)
+                at_out[(size_t)gi * 2 * nB + i] = i < nB ? 0.0 : 1.0;
         return;
     }
     // L from the row-major lower triangle (photoz_gp.py:251-253)
@@ -276,6 +281,17 @@ __global__ void __launch_bounds__(PRED_THREADS) gp_predict_kernel(
         nvar[node] = kd - q;
     }
     __syncthreads();
+    if (at_out) {
+        // predictAndInterpolate(np.array([z_i])) of the cross-validation in delight-learn.py:92-94:
+        // the same node values interpolated at ONE redshift per galaxy -> [mean(nB), var(nB)]
+        const double zv = zeval[gi];
+        const int lo = bin_left(gm.zGP, nzg, zv);
+        for (int b = tid; b < nB; b += PRED_THREADS) {
+            at_out[(size_t)gi * 2 * nB + b] = lin_interp(gm.zGP, nmean + b * nzg, lo, zv);
+            at_out[(size_t)gi * 2 * nB + nB + b] = lin_interp(gm.zGP, nvar + b * nzg, lo, zv);
+        }
+    }
+    if (!grid) return;
     // coarse -> fine grid, linear (photoz_gp.py:321-335), into the fused layout
     for (int i = tid; i < nB * nzp; i += PRED_THREADS) {
         const int b = i / nzp, zf = i % nzp;
@@ -361,7 +377,36 @@ int dl_gp_predict_dev(long long nT, long long nB, long long nt, long long nzg, l
     DL_CUDA_CHECK(cudaFuncSetAttribute(gp_predict_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     gp_predict_kernel<<<(unsigned)nT, PRED_THREADS, smem, (cudaStream_t)stream>>>(
-        gm, (int)nT, rows, (int)numCol, nzp, grid, train_z);
+        gm, (int)nT, rows, (int)numCol, nzp, grid, train_z, nullptr, nullptr);
+    DL_CUDA_CHECK(cudaGetLastError());
+    dl_count_launch();
+    return DL_OK;
+}
+
+// Same GP, evaluated at ONE redshift per galaxy: z_eval [nT] -> out [nT][2 nB] (band means, then
+// band variances).  delight-learn.py:92-94 calls predictAndInterpolate(np.array([z]), ell=ell)
+// with the galaxy's own redshift for the cross-validation chi2 (:95-100).
+int dl_gp_predict_at_dev(long long nT, long long nB, long long nt, long long nzg, long long nz,
+                         const double* KC_grid, const double* KL_grid, const double* KC_diag,
+                         const double* KL_diag, const double* zGP, const double* fzGrid,
+                         const double* tmpl, const double* zgrid, double V_C, double V_L,
+                         const double* rows, long long numCol, const double* z_eval, double* out,
+                         void* stream) {
+    GPModel gm;
+    int rc = gp_model(gm, nB, nzg, nt, nz, KC_grid, KL_grid, KC_diag, KL_diag, zGP, fzGrid, tmpl,
+                      zgrid, V_C, V_L);
+    if (rc) return rc;
+    if (nT == 0) return DL_OK;
+    DL_REQUIRE(KC_diag && KL_diag && rows && z_eval && out, "null pointer");
+    DL_REQUIRE(nB <= GP_MAXB, "at most 32 bands");
+    DL_REQUIRE(numCol >= 3 + nB + nt + nB * (nB + 1) / 2 + nB, "numCol too small");
+    const size_t smem = sizeof(double) * (GP_MAXB * (GP_MAXB + 1) + GP_MAXB + 2 * (size_t)nB * nzg +
+                                          (size_t)GP_MAXB * PRED_THREADS);
+    DL_REQUIRE(smem <= 220 * 1024, "nB * nzGP too large for shared memory");
+    DL_CUDA_CHECK(cudaFuncSetAttribute(gp_predict_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    gp_predict_kernel<<<(unsigned)nT, PRED_THREADS, smem, (cudaStream_t)stream>>>(
+        gm, (int)nT, rows, (int)numCol, 0, nullptr, nullptr, z_eval, out);
     DL_CUDA_CHECK(cudaGetLastError());
     dl_count_launch();
     return DL_OK;

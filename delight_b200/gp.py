@@ -115,6 +115,28 @@ class PhotozGPBatched:
         return ModelGrid(grid, nT, self.nB, self.nz), train_z
 
 
+    def predict_at(self, rows, z_eval):
+        """The GP of every row evaluated at ONE redshift each (photoz_gp.py:293-347 with
+        redshiftGrid = [z], as the cross-validation of delight-learn.py:92-94 calls it):
+        returns (mean [nT, nB], var [nT, nB]) as NumPy arrays."""
+        torch = _lib.require_cuda()
+        if not isinstance(rows, torch.Tensor):
+            rows = torch.from_numpy(np.ascontiguousarray(rows, dtype=np.float64))
+        rows = rows.cuda().contiguous()
+        nT, numCol = rows.shape
+        ze = torch.from_numpy(np.ascontiguousarray(z_eval, dtype=np.float64)).cuda()
+        if ze.numel() != nT:
+            raise ValueError("z_eval must have one redshift per row")
+        out = torch.empty((nT, 2 * self.nB), dtype=torch.float64, device="cuda")
+        _lib.check(_lib.lib().dl_gp_predict_at_dev(
+            nT, self.nB, self.nt, self.nzg, self.nz, _lib.ptr(self.KC), _lib.ptr(self.KL),
+            _lib.ptr(self.KCd), _lib.ptr(self.KLd), _lib.ptr(self.d_zgp), _lib.ptr(self.d_fz),
+            _lib.ptr(self.d_tmpl), _lib.ptr(self.d_zgrid), self.V_C, self.V_L, _lib.ptr(rows),
+            numCol, _lib.ptr(ze), _lib.ptr(out), _lib.stream_ptr()))
+        out = out.cpu().numpy()
+        return out[:, :self.nB], out[:, self.nB:]
+
+
 def catalogue(fluxes, fluxes_var, bands, nf, z):
     """Packed training catalogue (same container as the targets)."""
     return Targets(fluxes, fluxes_var, bands, nf, z)

@@ -225,6 +225,16 @@ int dl_gp_predict_dev(long long nT, long long nB, long long nt, long long nzg, l
                       const double* rows, long long numCol, double* grid, double* train_z,
                       void* stream);
 
+/* The same GP evaluated at ONE redshift per training galaxy   replaces delight-learn.py:92-94
+ * (predictAndInterpolate(np.array([z]), ell=ell) of the cross-validation): z_eval [nT] ->
+ * out [nT][2 nB] = band means then band variances. */
+int dl_gp_predict_at_dev(long long nT, long long nB, long long nt, long long nzg, long long nz,
+                         const double* KC_grid, const double* KL_grid, const double* KC_diag,
+                         const double* KL_diag, const double* zGP, const double* fzGrid,
+                         const double* tmpl, const double* zgrid, double V_C, double V_L,
+                         const double* rows, long long numCol, const double* z_eval, double* out,
+                         void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Measurement hooks (used by bench.py; no effect on results)
  * ---------------------------------------------------------------------------------------- */

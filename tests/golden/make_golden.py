@@ -13,6 +13,10 @@ Writes
     tests/golden/sdss_pipeline.npz     seeded mock -> reference learn -> predict -> apply epilogue
                                        (5 SDSS bands, training on 3, heterogeneous targets)
     tests/golden/templatefit.npz       templateFitting.py-equivalent (config 2 twin)
+    tests/golden/cv_small.npz          the CV file the real delight-learn.py writes with
+                                       crossValidate on (training catalogue of sdss_pipeline.npz;
+                                       `python tests/golden/make_golden.py cv`, not in the default
+                                       list so that the other fixtures stay byte-identical)
     tests/golden/compressed_small.npz  second ("compressed") pass of delight-apply.py:123-135:
                                        the reference's NumPy twin on the stored top-K columns
     delight_b200/data/lsst_cww.npz     LSST ugrizy Gaussian coefficients + CWW template flux
@@ -402,6 +406,38 @@ def gen_templatefit(wd):
     print("templatefit: %d targets" % n)
 
 
+def gen_cv(wd):
+    """Cross-validation of delight-learn (delight-learn.py:50-57,92-100,131-132): the real script,
+    crossValidate on, on the training catalogue of sdss_pipeline.npz (training on U, G, I;
+    held-out bands R, Z) -> the CV file it writes."""
+    g = np.load(os.path.join(GOLD, "sdss_pipeline.npz"))
+    cfg = pipeline.make_workdir(wd, bands=pipeline.SDSS,
+                                train_bands=["U_SDSS", "G_SDSS", "I_SDSS"], refband="I_SDSS",
+                                numObjects=24, dz=0.01, nzGP=40, Ncompress=8, copy_data=False)
+    pipeline.write_preprocessed(wd, pipeline.SDSS, g["amp"], g["mu"], g["sig"], g["tmpl"])
+    # the simulator leaves the held-out columns at 0 (and the script then fails on the empty band
+    # list, SURVEY 8c): give R and Z deterministic fluxes; one galaxy keeps a missing R
+    tr = g["train_cat"].copy()
+    tr[:, 2] = np.sqrt(np.abs(tr[:, 1] * tr[:, 3])) * (1 + 0.03 * np.sin(np.arange(tr.shape[0])))
+    tr[:, 4] = 1.1 * tr[:, 3] * (1 + 0.03 * np.cos(np.arange(tr.shape[0])))
+    tr[:, 7] = (0.05 * tr[:, 2]) ** 2
+    tr[:, 9] = (0.05 * tr[:, 4]) ** 2
+    tr[3, 2] = np.sqrt(tr[3, 0] * tr[3, 3])       # row 3 has G = -1
+    tr[3, 7] = (0.05 * tr[3, 2]) ** 2
+    tr[5, 2] = 0.0                                # R missing for one galaxy
+    np.savetxt(wd + "/galaxies-fluxredshifts.txt", tr)
+    np.savetxt(wd + "/galaxies-fluxredshifts2.txt", g["target_cat"])
+    txt = open(cfg).read().replace("crossValidate: False", "crossValidate: True")
+    open(cfg, "w").write(txt)
+    pipeline.run_script("delight-learn", cfg)
+    cv = np.loadtxt(wd + "/galaxies-gpCV.txt", ndmin=2)
+    rows = np.loadtxt(wd + "/galaxies-gpparams.txt")
+    assert np.allclose(rows, g["gp_rows"], rtol=2e-12, atol=1e-300)
+    assert cv.shape == (g["train_cat"].shape[0], 2) and np.all(cv <= 0) and np.any(cv < 0)
+    np.savez_compressed(os.path.join(GOLD, "cv_small.npz"), cv=cv, train_cat=tr)
+    print("cv_small:", cv.shape, "min", cv.min())
+
+
 def gen_lsst_data(wd):
     """LSST ugrizy coefficients + CWW template tables on the 1500-point grid (bench inputs)."""
     from delight.io import parseParamFile, readBandCoefficients, createGrids
@@ -439,6 +475,9 @@ if __name__ == "__main__":
             amp, mu, sig = gen_sdss_pipeline(wd)
             gen_templatefit(wd)
             gen_kernelparts_small(amp, mu, sig)
+    if "cv" in which:
+        with tempfile.TemporaryDirectory(prefix="delight_gold_") as wd:
+            gen_cv(wd)
     if "lsst" in which:
         with tempfile.TemporaryDirectory(prefix="delight_gold_") as wd:
             gen_lsst_data(wd)

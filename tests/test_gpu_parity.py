@@ -921,3 +921,175 @@ def test_pipeline_second_pass_uses_stored_indices(orc, sdss, tmp_path):
     b = first["pdfs"][:n] / first["pdfs"][:n].sum(axis=1, keepdims=True)
     assert np.abs(a - b).max() < 0.05 * b.max()
     assert second["metrics"].shape == first["metrics"].shape
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: drivers (cross-validation, template fitting), gpparams line numbers, G10-style targets,
+# config-5-shaped slice
+# ------------------------------------------------------------------------------------------------
+def _sdss_workdir(g, wd, train_cat=None, **kw):
+    from oracle import pipeline as refpipe
+    K = int(g["Ncompress"])
+    cfg = refpipe.make_workdir(wd, bands=refpipe.SDSS,
+                               train_bands=["U_SDSS", "G_SDSS", "I_SDSS"], refband="I_SDSS",
+                               numObjects=24, dz=0.01, nzGP=40, Ncompress=K, copy_data=False, **kw)
+    refpipe.write_preprocessed(wd, refpipe.SDSS, g["amp"], g["mu"], g["sig"], g["tmpl"])
+    np.savetxt(wd + "/galaxies-fluxredshifts.txt", g["train_cat"] if train_cat is None else train_cat)
+    np.savetxt(wd + "/galaxies-fluxredshifts2.txt", g["target_cat"])
+    return cfg
+
+
+def test_pipeline_learn_crossvalidate_same_file_as_reference(sdss, golden, tmp_path):
+    """`crossValidate: True` (delight-learn.py:50-57,92-100,131-132): the CV file of the batched
+    learn against the one the real script wrote (tests/golden/cv_small.npz)."""
+    from delight_b200 import pipeline
+    cvg = golden("cv_small")
+    wd = str(tmp_path)
+    cfg = _sdss_workdir(sdss, wd, train_cat=cvg["train_cat"])
+    txt = open(cfg).read().replace("crossValidate: False", "crossValidate: True")
+    open(cfg, "w").write(txt)
+    rows, cv = pipeline.learn(cfg)
+    np.testing.assert_allclose(rows, sdss["gp_rows"], rtol=1e-9,
+                               atol=1e-11 * np.abs(sdss["gp_rows"]).max())
+    np.testing.assert_allclose(cv, cvg["cv"], rtol=1e-9)
+    np.testing.assert_allclose(np.loadtxt(wd + "/galaxies-gpCV.txt"), cvg["cv"], rtol=1e-9)
+    assert cv[5, 0] == 0.0 and np.all(cv[:, 1] < 0)
+
+
+def test_pipeline_template_fit_same_files_as_reference(sdss, golden, tmp_path):
+    """python -m delight_b200.pipeline templatefit: scripts/templateFitting.py through the fused
+    kernel with the p(z,t) prior computed on the device (templateFitting.py:79-83), against the
+    script's own PDFs and computeMetrics rows (tests/golden/templatefit.npz)."""
+    from delight_b200 import pipeline
+    g = golden("templatefit")
+    wd = str(tmp_path)
+    cfg = _sdss_workdir(sdss, wd)
+    out = pipeline.template_fit(cfg)
+    n = g["pdfs"].shape[0]
+    np.testing.assert_allclose(out["pdfs"][:n], g["pdfs"], rtol=RTOL,
+                               atol=1e-290 * g["pdfs"].max())
+    np.testing.assert_allclose(out["metrics"][:n], g["metrics"], rtol=RTOL)
+    txt = np.loadtxt(wd + "/redshiftpdfs-cww.txt")
+    np.testing.assert_allclose(txt[:n], g["pdfs"], rtol=6e-3, atol=1e-300)
+    assert np.loadtxt(wd + "/metrics-cww.txt").shape == (txt.shape[0], g["metrics"].shape[1])
+
+
+def test_pipeline_compress_indices_are_gpparams_line_numbers(sdss, tmp_path):
+    """A gpparams file with an all-zero row in the MIDDLE (what multi-rank learn leaves behind a
+    skipped galaxy): the compress files must hold line numbers of that file
+    (targetIndices[sortind], delight-apply.py:150-153), and the second pass must find the same
+    training galaxies through them."""
+    from delight_b200 import pipeline
+    g = sdss
+    wd = str(tmp_path)
+    cfg = _sdss_workdir(g, wd)
+    rows = pipeline.learn(cfg)
+    nT = g["gp_rows"].shape[0]
+    hole = 7
+    with_hole = np.concatenate([rows[:hole], np.zeros((1, rows.shape[1])), rows[hole:nT]])
+    fmt = "%i " + "%.12e " * (rows.shape[1] - 1)
+    np.savetxt(wd + "/galaxies-gpparams.txt", rows[:nT], fmt=fmt)
+    base = pipeline.apply(cfg, write=False)
+    np.savetxt(wd + "/galaxies-gpparams.txt", with_hole, fmt=fmt)
+    first = pipeline.apply(cfg)
+    n = g["pdfs"].shape[0]
+    shifted = np.where(base["top_idx"][:n] >= hole, base["top_idx"][:n] + 1, base["top_idx"][:n])
+    np.testing.assert_array_equal(first["top_idx"][:n], shifted)
+    assert not np.any(first["top_idx"][:n] == hole)
+    np.testing.assert_array_equal(np.loadtxt(wd + "/compressIndices.txt", dtype=np.int64)[:n],
+                                  shifted)
+    np.testing.assert_allclose(first["pdfs"][:n], base["pdfs"][:n], rtol=1e-12, atol=1e-300)
+    second = pipeline.apply(cfg)                      # compressed pass through the stored lines
+    np.testing.assert_array_equal(np.sort(second["top_idx"][:n], axis=1),
+                                  np.sort(first["top_idx"][:n], axis=1))
+
+
+def test_fused_g10_style_target_catalogue(orc):
+    """G10-style TARGET catalogue (parameter_files/parameters_G10.cfg:11: 28 bands, every galaxy
+    keeps a random subset of 2..21 of them, io.py:331-337): >= 2k targets in one launch per band
+    COUNT, every target checked against the oracle."""
+    from delight_b200 import apply
+    rng = np.random.default_rng(28)
+    nO, nT, nz, nB = 2304, 48, 160, 28
+    zgrid = np.linspace(0.01, 3.0, nz)
+    mm = 1e5 * rng.uniform(0.5, 2.0, (1, nT, nB)) * (1 + 0.5 * np.sin(
+        zgrid[:, None, None] * rng.uniform(1, 4, (1, nT, nB))))
+    mc = (mm * rng.uniform(1e-3, 5e-2, (nz, nT, nB))) ** 2
+    zt = rng.uniform(0.01, 3.0, nT)
+    nfs = rng.integers(2, 22, nO)
+    bands = np.zeros((nO, nB), dtype=np.int64)
+    fl = np.zeros((nO, nB))
+    fv = np.zeros((nO, nB))
+    src, zi = rng.integers(0, nT, nO), rng.integers(0, nz, nO)
+    for o in range(nO):
+        b = np.sort(rng.choice(nB, nfs[o], replace=False))
+        bands[o, :nfs[o]] = b
+        true = mm[zi[o], src[o], b] * 4e-10
+        fv[o, :nfs[o]] = (0.05 * true) ** 2
+        fl[o, :nfs[o]] = true * (1 + 0.05 * rng.standard_normal(nfs[o]))
+    K = 10
+    grid = apply.ModelGrid.from_legacy(mm, mc)
+    t = apply.Targets(fl, fv, bands, nfs)
+    assert len(list(t.groups())) > 1500                  # almost every target has its own set
+    res = apply.apply_fused(grid, grid.gaussian_prior(zgrid, zt, 0.5), zgrid, t, ell_hat=1.0,
+                            ell_var=0.25, K=K, want_evid=True)
+    assert res["fused_launches"] == np.unique(nfs).size <= 20
+    ref = orc.apply_fused(fl, fv, nfs, bands, mm, mc, orc.z_prior(zgrid, zt, 0.5), zgrid,
+                          np.ones(nz), np.full(nz, 0.25), K, want_evid=True)
+    _check_fused(res, ref, K)
+    assert (res["top_idx"][:, 0] == src).mean() > 0.8
+
+
+def test_fused_config5_shaped_slice_vs_compiled_reference():
+    """Config-5 shape in the training dimension: 100k training galaxies, 4352 targets cut into
+    several workspace tiles (8 B x nT of raw evidences per target), 6 bands; a 16-target
+    subsample against the COMPILED reference operator + the script's epilogue
+    (delight-apply.py:137-153), the rest through size-independent properties."""
+    import torch
+    from oracle import ref
+    from delight_b200 import apply
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    ref.load()
+    from delight.utils_cy import approx_flux_likelihood_cy as cy_like
+    nO, nT, nz, nB, K = 4352, 100000, 300, 6, 50
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    zgrid = 0.01 + 0.01 * np.arange(nz)
+    base = 0.5 + 1.5 * torch.rand((1, nT, nB), generator=gen, device="cuda", dtype=torch.float64)
+    freq = 2 + 4 * torch.rand((1, nT, nB), generator=gen, device="cuda", dtype=torch.float64)
+    zz = torch.from_numpy(zgrid).cuda()[:, None, None]
+    mean = 1e5 * base * (1 + 0.6 * torch.sin(zz * freq))          # legacy layout [nz, nT, nB]
+    var = (mean * 0.01) ** 2
+    zt = np.random.default_rng(6).uniform(0.01, 3.0, nT)
+    grid = apply.ModelGrid.from_legacy(mean, var)
+    prior = grid.gaussian_prior(zgrid, zt, 0.5)
+    rng = np.random.default_rng(7)
+    src, zi = rng.integers(0, nT, nO), rng.integers(0, nz, nO)
+    true = mean[torch.from_numpy(zi).cuda(), torch.from_numpy(src).cuda()].cpu().numpy() * 4e-10
+    fl = true * (1 + 0.02 * rng.standard_normal(true.shape))
+    fv = (0.02 * true) ** 2
+    ws = apply.FusedWorkspace(max_bytes=3 << 29)                  # 1.5 GB: ~1.8k targets per call
+    res = apply.apply_fused(grid, prior, zgrid, apply.Targets.full(fl, fv), ell_hat=1.0,
+                            ell_var=0.25, K=K, workspace=ws)
+    assert res["fused_launches"] >= 3
+    # the source galaxy is among the K best of (nearly) every target; with 100k competitors and
+    # 2 % noise it is not always THE best
+    assert (res["top_idx"] == src[:, None]).any(axis=1).mean() > 0.9
+    assert np.all(np.diff(res["top_ev"], axis=1) <= 0)
+    assert np.isfinite(res["pdf"]).all() and (res["pdf"] >= 0).all()
+    # 16 targets spread over all tiles against the compiled reference
+    sub = np.linspace(0, nO - 1, 16).astype(int)
+    mm, mc = mean.cpu().numpy(), var.cpu().numpy()
+    pr = np.exp(-0.5 * ((zgrid[:, None] - zt[None, :]) / 0.5) ** 2)
+    for o in sub:
+        like = np.zeros((nz, nT))
+        cy_like(like, nz, nT, nB, fl[o], fv[o], mm, mc, ell_hat=np.ones(nz),
+                ell_var=np.full(nz, 0.25))
+        like *= pr
+        pdf = like.sum(axis=1)
+        ev = np.trapz(like, x=zgrid, axis=0)
+        idx = np.argsort(ev, kind="stable")[::-1][:K]
+        assert_close(res["pdf"][o][None], pdf[None], pdf.max() * 1e-290)
+        solid = ev[idx] > 1e-250 * ev[idx[0]]
+        np.testing.assert_array_equal(res["top_idx"][o][solid], idx[solid])
+        np.testing.assert_allclose(res["top_ev"][o][solid], ev[idx][solid], rtol=RTOL)
