@@ -34,17 +34,49 @@ N_COMPRESS = 50
 ELL_VAR = 0.25            # ellPriorSigma 0.5 (tests/parametersTest.cfg:57)
 Z_PRIOR_SIGMA = 0.5
 FLOP_PER_CELL = lambda nf: 27 * nf + 30     # SURVEY.md 8(d), fused path
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE fused_like_kernel launch at the default
-# configuration, from `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` on a B200
-# (profiles/r1_fused_like_dram_traffic.csv, grid 3756 x 4): 4.24 GB read (1.6 GB grid + prior,
-# re-read a few times over the launch, L2 hit rate 94 %) + 19.78 GB written (per-z-chunk evidence
-# partials, 12 x 16 B per (target, training), + the PDF partials).
-NCU_TRAFFIC_BYTES_DEFAULT_CONFIG = 4237682176 + 19782158336
+KERNEL_SOURCES = ["delight_b200/csrc/like_fused_kernel.cuh", "delight_b200/csrc/like_fused.cu",
+                  "delight_b200/csrc/common.cuh"]
+TRAFFIC_RECORD = os.path.join(REPO, "profiles", "r2_fused_traffic.json")
+
+
+def kernel_source_hash():
+    import hashlib
+    h = hashlib.sha256()
+    for f in KERNEL_SOURCES:
+        h.update(open(os.path.join(REPO, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(nO, nT, nz, nB):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE main-pass launch of the fused kernel,
+    from the committed ncu capture profiles/r2_fused_traffic.json (tools/traffic_record.py).
+    The record carries the launch shape and a hash of the kernel sources: it is only reported
+    for the same shape, and flagged when the sources changed since the capture."""
+    try:
+        rec = json.load(open(TRAFFIC_RECORD))
+    except Exception:
+        return None, "no capture (profiles/r2_fused_traffic.json missing)"
+    if list(rec.get("shape", [])) != [nO, nT, nz, nB]:
+        return None, "capture is for shape %s" % rec.get("shape")
+    note = "ncu capture %s: read %.2f GB + written %.2f GB" % (
+        rec.get("when", "?"), rec["dram_bytes_read"] / 1e9, rec["dram_bytes_write"] / 1e9)
+    if rec.get("kernel_source_hash") != kernel_source_hash():
+        note += " (kernel sources changed since the capture)"
+    return rec["dram_bytes_read"] + rec["dram_bytes_write"], note
 
 
 def workload_name(nO, nT, nz, nB):
     return ("C3 approx_flux_likelihood fused PDF+top-%d: %d targets x %d training GPs x %d z "
             "x %d bands (LSST ugrizy), f64" % (N_COMPRESS, nO, nT, nz, nB))
+
+
+def shared_config(nO, nT, nz, nB):
+    """The `config` of the JSON line: identical (keys and values) for both arms."""
+    return {"workload": workload_name(nO, nT, nz, nB), "targets_per_gpu": nO, "n_train": nT,
+            "nz": nz, "bands": nB, "Ncompress": N_COMPRESS,
+            "l2": "inputs larger than L2: model grid 2 x nz x n_train x bands x 8 B = %.2f GB, "
+                  "re-streamed every step" % (2.0 * nz * nT * nB * 8 / 1e9),
+            "parallelism": "targets sharded by rank, no data-path collective"}
 
 
 class ClockSampler:
@@ -186,10 +218,10 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(N_TARGETS, nT, nz, nB),
-                   "inputs": "larger than L2 (model grid 2 x %.0f MB)" % (model_mean.nbytes / 1e6),
-                   "model_grid": "reference learn + predictAndInterpolate on %d mock training "
-                                 "galaxies, %.0f s on the host (untimed setup)" % (nT, t_setup)},
+        "config": shared_config(args.targets, nT, nz, nB),
+        "arm_notes": {"model_grid": "reference learn + predictAndInterpolate on %d mock training "
+                                    "galaxies, %.0f s on the host (untimed setup)" % (nT, t_setup),
+                      "sample": "%d targets per step" % per_step},
         "cpu_baseline": {"value": value, "unit": "galaxies/s", "cores": cores, "kind": kind,
                          "sample": "%d targets/step against the full %d x %d x %d grid, loop "
                                    "body of delight-apply.py:114-162 incl. its per-target "
@@ -255,40 +287,113 @@ def parity_check(gpu, outs):
             "tolerance": 1e-9}
 
 
-def other_configs(data):
-    """Secondary BASELINE.json configurations, timed once each (CUDA events, inputs resident):
-    config 2 (templateFitting-equivalent, 100k targets x 8 templates x 1500 z x 5 bands) and
-    config 4 (delight-learn on 100k training galaxies, 28 bands with 2..21 valid per galaxy)."""
+def _ev_ms(fn, reps=1):
     import torch
-    from delight_b200 import apply, gp as gpmod
-    out = {}
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # ---- config 2
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, out
+
+
+def config2_templatefit(data, budget_s=6.0):
+    """BASELINE.json configs[1]: templateFitting.py-equivalent, 100k targets x 8 CWW templates x
+    1500 z x 5 bands (ugriz).  Resident and end-to-end (pinned-host catalogue in, 1.2 GB of PDFs
+    + metrics out) timings, the reference's own loop body (NumPy twin, p(z,t) prior, sum,
+    computeMetrics; templateFitting.py:60-89) timed on a sample of the same targets, and the
+    GPU-vs-reference error on that sample."""
+    import torch
+    from delight_b200 import apply
     zgrid, tmpl = data["zgrid"], data["tmpl"][:, :5]
     nt, nB, nz = tmpl.shape
     f_mod = np.ascontiguousarray(tmpl.transpose(2, 0, 1))
-    b2 = data["p_z_t"] ** 2
-    p_z = data["p_t"][None, :] * zgrid[:, None] / b2[None, :] * np.exp(
-        -0.5 * zgrid[:, None] ** 2 / b2[None, :])                    # templateFitting.py:79-82
     grid = apply.ModelGrid.from_legacy(f_mod, np.zeros_like(f_mod))
-    prior = grid.explicit_prior(p_z)
+    prior = grid.template_prior(zgrid, data["p_t"], data["p_z_t"])      # templateFitting.py:79-83
     rng = np.random.default_rng(3)
     nO = 100000
-    fl = f_mod[rng.integers(0, nz, nO), rng.integers(0, nt, nO)] * rng.uniform(.5, 2, (nO, 1))
+    ztrue = zgrid[rng.integers(0, nz, nO)]
+    fl = f_mod[np.searchsorted(zgrid, ztrue), rng.integers(0, nt, nO)] * rng.uniform(.5, 2, (nO, 1))
     fl = fl * (1 + 0.05 * rng.standard_normal(fl.shape))
-    tg = apply.Targets.full(fl, (0.05 * fl) ** 2).to_device()
+    fv = (0.05 * fl) ** 2
     ws = apply.FusedWorkspace()
-    run = lambda: apply.apply_fused(grid, prior, zgrid, tg, ell_hat=1.0, ell_var=1e24, K=0,
-                                    want_metrics=True, workspace=ws, out_device=True)
+    CL = [0.1, 0.5, 0.68, 0.95]
+    tg = apply.Targets.full(fl, fv, ztrue).to_device()
+    run = lambda t=tg: apply.apply_fused(grid, prior, zgrid, t, ell_hat=1.0, ell_var=1e24, K=0,
+                                         want_metrics=True, confidence_levels=CL, workspace=ws,
+                                         out_device=True)
     run()
-    ev0.record(); run(); ev1.record(); torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1)
-    out["c2_templatefit"] = {"workload": "100k targets x 8 CWW templates x 1500 z x 5 bands, "
-                             "PDF + metrics", "galaxies_per_s": nO / (ms * 1e-3), "ms": ms}
-    del grid, prior, tg
-    # ---- config 4
+    ms, res = _ev_ms(run, 2)
+    # end to end: host catalogue in, PDFs + metrics out
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_fl, h_fv = pin(fl), pin(fv)
+    h_pdf = torch.empty((nO, nz), dtype=torch.float64).pin_memory()
+    h_met = torch.empty((nO, 8 + len(CL)), dtype=torch.float64).pin_memory()
+
+    def e2e():
+        t = apply.Targets.full(h_fl.numpy(), h_fv.numpy(), ztrue)
+        t._dev = {("nf", nB): (h_fl.cuda(non_blocking=True), h_fv.cuda(non_blocking=True), None,
+                               None)}
+        r = run(t)
+        h_pdf.copy_(r["pdf"], non_blocking=True)
+        h_met.copy_(r["metrics"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e2e()
+    t0 = time.perf_counter()
+    e2e()
+    e2e_s = time.perf_counter() - t0
+    out = {"workload": "C2 templateFitting-equivalent: 100k targets x 8 CWW templates x 1500 z x "
+                       "5 bands, PDF + computeMetrics (4 confidence levels)",
+           "galaxies_per_s": nO / (ms * 1e-3), "ms": ms,
+           "e2e_galaxies_per_s": nO / e2e_s, "e2e_ms": e2e_s * 1e3,
+           "h2d_bytes": h_fl.numel() * 16, "d2h_bytes": h_pdf.numel() * 8 + h_met.numel() * 8}
+    # the reference's loop body on the host, same targets
+    try:
+        from oracle import ref
+        if ref.available():
+            ref.load()
+            from delight.utils import approx_flux_likelihood, computeMetrics
+            b2 = data["p_z_t"] ** 2
+            p_z = data["p_t"][None, :] * zgrid[:, None] / b2[None, :] * np.exp(
+                -0.5 * zgrid[:, None] ** 2 / b2[None, :])
+            pdfs, mets, n, t0 = [], [], 0, time.perf_counter()
+            while n < 256 and (time.perf_counter() - t0 < budget_s or n < 4):
+                like = approx_flux_likelihood(fl[n], fv[n], f_mod, normalized=True,
+                                              marginalizeEll=True, ell_hat=1,
+                                              ell_var=(1 * 1e12) ** 2)
+                like *= p_z
+                pdfs.append(like.sum(axis=1))
+                mets.append(computeMetrics(ztrue[n], zgrid, pdfs[-1], CL))
+                n += 1
+            dt = time.perf_counter() - t0
+            pr, mr = np.stack(pdfs), np.stack(mets)
+            g_pdf, g_met = res["pdf"][:n].cpu().numpy(), res["metrics"][:n, :mr.shape[1]].cpu().numpy()
+            big = pr > 1e-290 * pr.max(axis=1, keepdims=True)
+            out["cpu_baseline"] = {"value": n / dt, "unit": "galaxies/s", "cores": 1,
+                                   "kind": "reference",
+                                   "sample": "%d targets, loop body of templateFitting.py:60-89 "
+                                             "(NumPy, single thread), %.1f s" % (n, dt)}
+            out["parity_check"] = {"targets": n,
+                                   "pdf_max_rel_err": float((np.abs(g_pdf - pr)[big] / pr[big]).max()),
+                                   "metrics_max_rel_err": float(np.abs(g_met / mr - 1).max()),
+                                   "tolerance": 1e-9}
+    except Exception as e:                                   # the checker must not sink the bench
+        out["cpu_baseline"] = {"error": repr(e)}
+    return out
+
+
+def config4_learn(data, full=False):
+    """BASELINE.json configs[3]: delight-learn on 100k synthetic training galaxies, 28 bands with
+    2..21 valid per galaxy (G10-style): kernel grids for 28 bands + batched template fit, K(X),
+    Cholesky, gpparams row.  full=True also times the reference (PhotozGP constructor = its
+    kernel-grid build, and its learn loop on a sample) and compares the rows."""
+    import torch
+    from delight_b200 import gp as gpmod
     rng = np.random.default_rng(4)
-    nB, NC, nzg, nT = 28, 7, 150, 100000
+    zgrid = data["zgrid"]
+    nz = zgrid.size
+    nB, NC, nT = 28, 7, 100000
     mu0 = np.linspace(3500, 22000, nB)
     amp = rng.uniform(0.2, 1.0, (nB, NC))
     mu = mu0[:, None] + np.linspace(-300, 300, NC)[None, :]
@@ -296,11 +401,10 @@ def other_configs(data):
     zgp = data["zgridGP"]
     tm = 1e-6 * rng.uniform(0.5, 2.0, (8, nB, 1)) * (1 + 0.5 * np.sin(
         zgrid[None, None, :] * rng.uniform(1, 5, (8, nB, 1))))
-    ev0.record()
-    gpm = gpmod.PhotozGPBatched(tm, zgrid, amp, mu, sig, [6500.0, 5002.26, 3732.22], 0.5, 0.5,
-                                1e3, 1e2, zgp)
-    ev1.record(); torch.cuda.synchronize()
-    grid_ms = ev0.elapsed_time(ev1)
+    lines = [6500.0, 5002.26, 3732.22]
+    mk = lambda: gpmod.PhotozGPBatched(tm, zgrid, amp, mu, sig, lines, 0.5, 0.5, 1e3, 1e2, zgp)
+    mk()
+    grid_ms, gpm = _ev_ms(mk)
     z = rng.uniform(0.05, 2.9, nT)
     nb = rng.integers(2, 22, nT)
     order = np.argsort(rng.random((nT, nB)), axis=1)
@@ -316,12 +420,126 @@ def other_configs(data):
     gpm.fit(cat, out_device=True)
     t0 = time.perf_counter(); rows = gpm.fit(cat, out_device=True); torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    ok = bool(torch.isfinite(rows).all().item())
-    out["c4_learn"] = {"workload": "100k training galaxies, 28 bands (2..21 valid each), "
-                       "template fit + K(X) + Cholesky + gpparams row; incl. H2D of the "
-                       "catalogue", "galaxies_per_s": nT / dt, "ms": dt * 1e3,
-                       "kernel_grid_28_bands_ms": grid_ms, "kernel_grid_pairs": nB * nB * nzg * nzg,
-                       "finite": ok}
+    out = {"workload": "C4 delight-learn: 100k training galaxies, 28 bands (2..21 valid each), "
+                       "template fit + K(X) + Cholesky + gpparams row; incl. H2D of the catalogue",
+           "galaxies_per_s": nT / dt, "ms": dt * 1e3, "kernel_grid_28_bands_ms": grid_ms,
+           "kernel_grid_pairs": nB * nB * zgp.size * zgp.size,
+           "finite": bool(torch.isfinite(rows).all().item())}
+    if full:
+        from oracle import ref, ref_pipeline
+        if ref.available():
+            d28 = dict(tmpl=tm, zgrid=zgrid, amp=amp, mu=mu, sig=sig, zgridGP=zgp)
+            hyper = dict(lines_pos=lines, lines_width=[20.0] * 3, V_C=0.5, V_L=0.5, alpha_C=1e3,
+                         alpha_L=1e2)
+            set_omp_threads(os.cpu_count() or 1)
+            t0 = time.perf_counter()
+            gp_ref, f_mod = ref_pipeline.make_gp(d28, hyper)
+            ctor_s = time.perf_counter() - t0
+            set_omp_threads(1)
+            n = 200
+            t0 = time.perf_counter()
+            rr = ref_pipeline.learn(gp_ref, f_mod, z[:n], bands[:n], nb[:n], fl[:n], fv[:n])
+            ls = time.perf_counter() - t0
+            got = rows[:n].cpu().numpy()
+            m = rr != 0
+            out["cpu_baseline"] = {"value": n / ls, "unit": "galaxies/s", "cores": 1,
+                                   "kind": "reference",
+                                   "sample": "%d galaxies through the reference's learn loop "
+                                             "(delight-learn.py:61-90), %.1f s; its PhotozGP "
+                                             "constructor (28-band kernel grids, OpenMP over %d "
+                                             "threads): %.1f s" % (n, ls, os.cpu_count() or 1,
+                                                                   ctor_s),
+                                   "kernel_grid_s": ctor_s}
+            out["parity_check"] = {"galaxies": n,
+                                   "rows_max_rel_err": float(np.abs(got[m] / rr[m] - 1).max()),
+                                   "band_lists_equal": bool(np.array_equal(got[:, :3 + nB] != 0,
+                                                                           rr[:, :3 + nB] != 0)),
+                                   "tolerance": 1e-9}
+    return out
+
+
+def config5_strong(data, grid_cache, world, rank, total_targets, nT=100000):
+    """BASELINE.json configs[4] scaled to a bench-sized slice: `total_targets` targets (STRONG
+    scaling: split over the ranks with the reference's formula) against 100k training GPs x 1500
+    z x 6 bands, model grid (14.7 GB) replicated per GPU.  Max-over-ranks device time."""
+    import torch
+    import torch.distributed as dist
+    from delight_b200 import apply, gp as gpmod, workloads
+    H = workloads.HYPER
+    zgrid = data["zgrid"]
+    nB = data["tmpl"].shape[1]
+    gpm = grid_cache["gpm"]
+    tr = workloads.mock_catalogue(nT, data, seed=11, ell=1e6)
+    tcat = gpmod.catalogue(tr["fluxes"], tr["fluxes_var"], np.tile(np.arange(nB), (nT, 1)),
+                           np.full(nT, nB), tr["z"])
+    t0 = time.perf_counter()
+    grid, train_z = gpm.predict(gpm.fit(tcat, out_device=True))
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t0
+    prior = grid.gaussian_prior(zgrid, train_z, Z_PRIOR_SIGMA)
+    first, last = apply.partition(total_targets, rank, world)
+    cat = workloads.mock_catalogue(total_targets, data, seed=12)
+    tg = apply.Targets.full(cat["fluxes"][first:last], cat["fluxes_var"][first:last]).to_device()
+    ws = apply.FusedWorkspace()
+    run = lambda: apply.apply_fused(grid, prior, zgrid, tg, ell_hat=1.0, ell_var=ELL_VAR,
+                                    K=N_COMPRESS, workspace=ws, out_device=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms, res = _ev_ms(run)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    del grid, prior
+    return {"workload": "C5-shaped slice, strong scaling: %d targets in all x %d training GPs x "
+                        "%d z x %d bands; model grid %.1f GB replicated per GPU"
+                        % (total_targets, nT, zgrid.size, nB,
+                           nT * (2 * nB + 1) * 1536 * 8 / 1e9),
+            "galaxies_per_s": total_targets / (ms * 1e-3), "ms": ms, "n_gpus": world,
+            "scaling": "strong", "fused_launches_per_rank": res["fused_launches"],
+            "model_grid_setup_s": setup_s}
+
+
+def config1_stock_scripts(n=300):
+    """BASELINE.json configs[0]: the reference's own delight-learn.py / delight-apply.py
+    (byte-compiled, unmodified) on an LSST-band mock of n + n objects -- once on the reference's
+    Cython operators, once with delight_b200's CUDA operators registered under the reference's
+    module names (drop-in mode).  Wall-clock per script; output files compared."""
+    import tempfile
+    from delight_b200 import workloads
+    from oracle import pipeline as refpipe, ref
+    if not ref.available():
+        return {"unavailable": "oracle/_ref not built"}
+    data = workloads.load_lsst()
+    out = {"workload": "C1 stock scripts: %d training + %d target galaxies, 6 LSST bands, "
+                       "1500 z, nzGP 150" % (n, n)}
+    files = {}
+    for mode in ("reference", "dropin"):
+        with tempfile.TemporaryDirectory(prefix="dl_c1_") as wd:
+            cfg = refpipe.make_workdir(wd, bands=refpipe.LSST, refband="lsst_i", zmin=0.01,
+                                       zmax=3.01, dz=0.002, nzGP=150, numObjects=n,
+                                       Ncompress=10, copy_data=False)
+            refpipe.write_preprocessed(wd, refpipe.LSST, data["amp"], data["mu"], data["sig"],
+                                       data["tmpl"])
+            for name, seed, ell in (("galaxies-fluxredshifts.txt", 21, 1e6),
+                                    ("galaxies-fluxredshifts2.txt", 22, 1.0)):
+                c = workloads.mock_catalogue(n, data, seed=seed, ell=ell, extra_frac=0.0)
+                np.savetxt(os.path.join(wd, name),
+                           np.column_stack([c["fluxes"], c["fluxes_var"], c["z"], c["types"]]))
+            t0 = time.perf_counter()
+            refpipe.run_script("delight-learn", cfg, omp_threads=1, dropin=mode == "dropin")
+            t1 = time.perf_counter()
+            refpipe.run_script("delight-apply", cfg, dropin=mode == "dropin")
+            t2 = time.perf_counter()
+            out[mode] = {"learn_s": t1 - t0, "apply_s": t2 - t1}
+            files[mode] = (np.loadtxt(os.path.join(wd, "galaxies-gpparams.txt")),
+                           np.loadtxt(os.path.join(wd, "redshiftpdfs.txt")))
+    a, b = files["reference"], files["dropin"]
+    m = a[0] != 0
+    out["parity_check"] = {"gpparams_max_rel_err": float(np.abs(b[0][m] / a[0][m] - 1).max()),
+                           "pdf_files_max_rel_err (%.2e text)": float(
+                               (np.abs(b[1] - a[1]) / np.maximum(np.abs(a[1]), 1e-300))[a[1] > 0].max())}
     return out
 
 
@@ -442,9 +660,22 @@ def run_b200(args):
     h2d = h_flux.numel() * 8 + h_var.numel() * 8
     d2h = h_pdf.numel() * 8 + h_idx.numel() * 8 + h_ev.numel() * 8
 
+    # ---- secondary configurations (BASELINE.json configs[0], [1], [3], [4]) ----------------------
     extras = None
-    if rank == 0 and world == 1 and not args.no_extras:
-        extras = other_configs(data)
+    if not args.no_extras:
+        extras = {}
+        if args.c5_targets > 0:          # every rank takes part (strong scaling over the ranks)
+            del resident
+            ws.buf = None
+            torch.cuda.empty_cache()
+            c5 = config5_strong(data, {"gpm": gpm}, world, rank, args.c5_targets)
+            if rank == 0:
+                extras["c5_strong"] = c5
+        if rank == 0 and world == 1:
+            extras["c2_templatefit"] = config2_templatefit(data)
+            extras["c4_learn"] = config4_learn(data, full=args.extras == "full")
+            if args.extras == "full":
+                extras["c1_stock_scripts"] = config1_stock_scripts()
     if rank == 0:
         peaks = measured_peaks()
         fp64 = ctypes.c_double(0)
@@ -453,20 +684,21 @@ def run_b200(args):
         k_ms = kms.value / max(kn.value, 1)
         achieved = cells_per_launch * FLOP_PER_CELL(nB) / (k_ms * 1e-3) * 1e-12
         grid_bytes = grid.grid.numel() * 8 + prior.numel() * 8
+        traffic, traffic_note = measured_traffic(nO, nT, nz, nB)
         roofline = {
-            "bound": "fp64", "kernel": "fused_like_kernel<%d,false,2>" % nB,
+            "bound": "fp64", "kernel": "fused_like_kernel<%d,false,false,MAIN>" % nB,
             "bound_note": "FP64 vector (FMA) pipe: no stage is a dense contraction (tensor cores "
                           "not applicable) and HBM traffic is 3 orders of magnitude below its "
                           "roofline (BASELINE.json metric: % of FP64/HBM roofline)",
             "achieved": achieved, "peak": fp64.value, "unit": "TFLOP/s",
             "frac": achieved / fp64.value if fp64.value else None,
             "peak_source": "measured live: dl_fp64_peak (dependent FMA chains, all SMs); "
-                           "MEASURED_PEAKS.json has no FP64 entry; datasheet 37.2 TFLOP/s",
+                           "MEASURED_PEAKS.json has no FP64 entry; datasheet 37.2 TFLOP/s "
+                           "(profiles/r2_fp64_peak.json)",
             "flop_per_cell": FLOP_PER_CELL(nB), "cells_per_launch": cells_per_launch,
             "kernel_ms": k_ms, "kernel_share_of_step": kms.value / ms_total,
-            "traffic": (NCU_TRAFFIC_BYTES_DEFAULT_CONFIG
-                        if (nO, nT) == (N_TARGETS, N_TRAIN) else None),
-            "traffic_unit": "bytes per launch (ncu dram read+write, profiles/)",
+            "traffic": traffic, "traffic_source": traffic_note,
+            "traffic_unit": "bytes per launch (ncu dram read + write of the main pass)",
             "hbm_algorithmic_bytes_per_launch": grid_bytes + nO * (2 * nB * 8 + nz * 8
                                                                   + N_COMPRESS * 16 + 64),
             "hbm_peak_GBs": peaks.get("hbm_gbs"),
@@ -488,16 +720,11 @@ def run_b200(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": workload_name(nO, nT, nz, nB),
-                       "targets_per_gpu": nO, "n_train": nT, "nz": nz, "bands": nB,
-                       "Ncompress": N_COMPRESS,
-                       "model_grid": "device learn + predict of %d simulateWithSEDs-style mock "
-                                     "training galaxies, replicated per GPU, %.2f GB"
-                                     % (nT, grid_bytes / 1e9),
-                       "setup": setup_ms,
-                       "l2": "inputs larger than L2 (model grid %.2f GB re-streamed per step)"
-                             % (grid_bytes / 1e9),
-                       "parallelism": "targets sharded by rank, no data-path collective"},
+            "config": shared_config(nO, nT, nz, nB),
+            "arm_notes": {"model_grid": "device learn + predict of %d simulateWithSEDs-style "
+                                        "mock training galaxies, replicated per GPU, %.2f GB in "
+                                        "the kernel's layout" % (nT, grid_bytes / 1e9),
+                          "setup": setup_ms},
             "e2e": {"value": e2e_value, "unit": "galaxies/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
@@ -524,6 +751,11 @@ def main():
                     help="reference arm: targets per step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary configurations")
+    ap.add_argument("--extras", default="default", choices=["default", "full"],
+                    help="full: also the reference baselines of config 4 and the stock scripts "
+                         "of config 1 (minutes of host time)")
+    ap.add_argument("--c5-targets", type=int, default=16384,
+                    help="targets IN ALL of the config-5-shaped strong-scaling extra (0: skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -699,11 +699,12 @@ int dl_like_fused_dev(long long nO, long long nT, long long nz, long long nB, in
     DL_CUDA_CHECK(cudaGetLastError());
     dl_count_launch();
 
-    int sm_count = 148;
+    int sm_count = 148, l2_bytes = 126 << 20;
     {
         int dev = 0;
         DL_CUDA_CHECK(cudaGetDevice(&dev));
         DL_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+        DL_CUDA_CHECK(cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, dev));
     }
     const int ftpc = cfg_warps(pl.cfg) * FTO;
     const int slots = sm_count * (pl.cfg == 0 ? 2 : 1);
@@ -718,7 +719,17 @@ int dl_like_fused_dev(long long nO, long long nT, long long nz, long long nB, in
     p.nU = n_union;
     p.nB = (int)nB; p.nz = (int)nz; p.nzp = nzp; p.nT = (int)nT; p.nO = (int)nO;
     p.nTiles = (int)((nO + ftpc - 1) / ftpc);
-    p.G = env_int("DL_FUSED_G", slots / 2 > 0 ? slots / 2 : 1);
+    // tiles per L2 group: their PDF rows (tile x nzp x 8 B each, updated with red.add at every
+    // chunk end) must stay L2-resident next to the training blocks in flight.  Measured at the
+    // bench shape (ncu dram bytes of one main pass, profiles/): a third of the L2 for the PDF
+    // rows (G = 111 of 32 targets) -> 5.0 GB read + 0.95 GB written; G = 148: 5.0 + 6.9 GB
+    // (rows evicted between flushes); G = 74: 8.4 + 1.2 GB (model grid re-read per group).
+    {
+        const long long tile_bytes = (long long)ftpc * nzp * 8;
+        long long g = (long long)l2_bytes / 3 / tile_bytes;
+        g = g < 4 ? 4 : (g > slots ? slots : g);
+        p.G = env_int("DL_FUSED_G", (int)g);
+    }
     p.stages = pl.stages;
 
     auto set_blocks = [&](long long nTlist, int stride, int TT) {

@@ -48,6 +48,12 @@ constexpr int ZJ = 2;         // redshifts a lane processes jointly (independent
 #ifndef DL_PREF
 #define DL_PREF 2
 #endif
+#ifndef DL_ROTPROD
+#define DL_ROTPROD 1
+#endif
+#ifndef DL_CHI2_EARLY
+#define DL_CHI2_EARLY 0
+#endif
 #ifndef DL_TJ2_NF
 #define DL_TJ2_NF 17
 #endif
@@ -60,7 +66,7 @@ enum { MODE_MAIN = 0, MODE_SAMPLE = 1 };
 __host__ __device__ constexpr int cfg_of(int nf, bool het) { return (het || nf >= DL_CFG1_NF) ? 1 : 0; }
 __host__ __device__ constexpr int cfg_warps(int cfg) { return cfg ? 16 : 8; }
 __host__ __device__ constexpr int cfg_fzc(int cfg) { return cfg ? 64 : 128; }
-__host__ __device__ constexpr int cfg_tt(int cfg) { return cfg ? 32 : 64; }     // default t-block
+__host__ __device__ constexpr int cfg_tt(int cfg) { return 32; }                // default t-block
 
 // per-target constants (doubles), s = sqrt(cov_scale / c), c = power of two near the variances:
 //   [0, 2NF)      (a_f s, w_f)          pass 0:  a = obs / var', w = 1 / var'
@@ -248,7 +254,12 @@ __device__ __forceinline__ void cells_xy(const double* const (&tcs)[TJ], const M
                 y[j][c] = rsqrt_fast(P[j][c] * ftt[j][c]);
                 rF = (y[j][c] * y[j][c]) * P[j][c];               // 1 / FTT
             }
+#if DL_CHI2_EARLY
+            // FOT^2 does not wait for 1/FTT: one dependent operation less behind the rsqrt
+            const double chi2 = fma(-(fot[j][c] * fot[j][c]), rF, foo[j][c]);
+#else
             const double chi2 = fma(-(fot[j][c] * rF), fot[j][c], foo[j][c]);
+#endif
             x[j][c] = fma(hc, chi2, xmask[j][c]);     // -chi2/2 - A in the target's units
         }
     }
@@ -397,6 +408,9 @@ fused_like_kernel(const FusedParams p) {
     };
     if (warp == 0)
         for (int j = 0; j < PREF; ++j) issue_ahead(j);
+#if DL_ROTPROD
+    int prod = 0;                                 // whose turn it is to issue (step mod FW)
+#endif
 
     // ---------------------------------------------------------------------- compute
     // Each lane works on PAIRS of redshifts (z, z+32) of the chunk for one target at a time:
@@ -413,7 +427,14 @@ fused_like_kernel(const FusedParams p) {
     const int var0 = nU * FZC;
 
     while (chunk < nchunk) {
+#if DL_ROTPROD
+        // the producer role rotates over the warps step by step, so that no warp is the
+        // permanent straggler the other seven wait for
+        if (warp == prod) issue_ahead(PREF);                              // warp-uniform
+        if (++prod == FW) prod = 0;
+#else
         if (warp == 0) issue_ahead(PREF);                                 // warp-uniform
+#endif
         mbar_wait(&full[cs], cph);
         const double* st = stage + (size_t)cs * ROWS * FZC;
         const int z0 = chunk * FZC;
@@ -596,8 +617,10 @@ fused_like_kernel(const FusedParams p) {
             if (p.rescue && p.flag[og] == 0) continue;         // warp-uniform
             if (p.evid != nullptr) {
                 double* dst = p.evid + (size_t)og * p.nT + ts0;
+                // streaming store: written once, read by the top-K kernel much later -- keep
+                // these lines from displacing the PDF accumulators and the model grid in L2
                 for (int q = lane; q < tcount; q += 32)
-                    dst[q] = E_sm[(size_t)(tfirst + o) * TTs + q];
+                    __stcs(dst + q, E_sm[(size_t)(tfirst + o) * TTs + q]);
             }
             if (lane == 0) {
                 atomicMax(p.Vbits + og, V_sm[tfirst + o]);

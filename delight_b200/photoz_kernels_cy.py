@@ -7,7 +7,7 @@ in-place outputs (e.g. KL_grid[b1, b2, :, :] as passed by delight/photoz_kernels
 import numpy as np
 
 from . import _lib
-from .utils_cy import _view, _dev
+from .utils_cy import _view, _dev, _dev_out
 
 __all__ = ["kernelparts", "kernelparts_diag", "kernel_parts_interp"]
 
@@ -53,7 +53,7 @@ def kernelparts(NO1, NO2, NC, NL, alpha_C, alpha_L, fcoefs_amp, fcoefs_mu, fcoef
     _check_bands(b1[:NO1], nB, "b1")
     _check_bands(b2[:NO2], nB, "b2")
     d_b1, d_f1, d_b2, d_f2 = _dev(b1[:NO1]), _dev(fz1[:NO1]), _dev(b2[:NO2]), _dev(fz2[:NO2])
-    d_out = [_dev(o[:NO1, :NO2]) for o in outs]
+    d_out = [_dev_out(o[:NO1, :NO2]) for o in outs]
     _lib.check(_lib.lib().dl_kernelparts_dev(
         NO1, NO2, NC, NL, float(alpha_C), float(alpha_L), _lib.ptr(d_amp), _lib.ptr(d_mu),
         _lib.ptr(d_sig), _lib.ptr(d_lm), _lib.ptr(d_nr), _lib.ptr(d_b1), _lib.ptr(d_f1),
@@ -81,7 +81,7 @@ def kernelparts_diag(NO1, NC, NL, alpha_C, alpha_L, fcoefs_amp, fcoefs_mu, fcoef
                                                 norms, NC, NL)
     _check_bands(b1[:NO1], nB, "b1")
     d_b1, d_f1 = _dev(b1[:NO1]), _dev(fz1[:NO1])
-    d_out = [_dev(o[:NO1]) for o in outs]
+    d_out = [_dev_out(o[:NO1]) for o in outs]
     _lib.check(_lib.lib().dl_kernelparts_diag_dev(
         NO1, NC, NL, float(alpha_C), float(alpha_L), _lib.ptr(d_amp), _lib.ptr(d_mu),
         _lib.ptr(d_sig), _lib.ptr(d_lm), _lib.ptr(d_nr), _lib.ptr(d_b1), _lib.ptr(d_f1),

@@ -26,7 +26,73 @@ def _view(a, dtype, ndim, name):
     return a
 
 
+class _UploadCache:
+    """Device copies of large read-only inputs, keyed by content.
+
+    The reference's callers hand the same big arrays to the operators over and over:
+    delight-apply.py:141-142 passes a FRESH fancy-indexed copy of the whole model grid per target
+    (1.44 GB at config 3) and Photoz_kernel.K calls kernel_parts_interp four times with the same
+    Kgrid (photoz_kernels.py:304-325).  Identity cannot be used (the copies are new objects, and
+    a caller may change an array in place), so the key is shape + dtype + a full-content
+    fingerprint: the wrap-around uint64 sum of all words and of the words weighted by a short
+    repeating pattern -- one pass over the host array at memory bandwidth, several times cheaper
+    than the pageable host-to-device copy it saves.  Least-recently-used entries are dropped
+    beyond `max_bytes`."""
+
+    MIN_BYTES = 1 << 20
+
+    def __init__(self, max_bytes=6 << 30):
+        self.max_bytes, self.bytes, self.hits, self.misses = max_bytes, 0, 0, 0
+        self.entries = {}          # key -> tensor (dict order = recency)
+        self._w = None
+
+    def _fingerprint(self, a):
+        w = a.view(np.uint64).reshape(-1) if a.dtype.itemsize == 8 else \
+            np.frombuffer(a.tobytes(), dtype=np.uint8).astype(np.uint64)
+        if self._w is None:
+            self._w = (np.arange(1, 4097, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15))
+        n = w.size // 4096 * 4096
+        with np.errstate(over="ignore"):
+            s0 = int(np.add.reduce(w, dtype=np.uint64))
+            s1 = int(np.add.reduce(np.add.reduce(w[:n].reshape(-1, 4096), axis=0,
+                                                 dtype=np.uint64) * self._w, dtype=np.uint64)) \
+                if n else 0
+        return s0, s1
+
+    def get(self, a):
+        torch = _lib.require_cuda()
+        a = np.ascontiguousarray(a)
+        if a.nbytes < self.MIN_BYTES:
+            return torch.from_numpy(a).cuda()
+        key = (a.shape, a.dtype.str) + self._fingerprint(a)
+        t = self.entries.pop(key, None)
+        if t is None:
+            self.misses += 1
+            t = torch.from_numpy(a).cuda()
+            self.bytes += a.nbytes
+            while self.bytes > self.max_bytes and self.entries:
+                old = self.entries.pop(next(iter(self.entries)))
+                self.bytes -= old.numel() * old.element_size()
+        else:
+            self.hits += 1
+        self.entries[key] = t
+        return t
+
+    def clear(self):
+        self.entries.clear()
+        self.bytes = 0
+
+
+_cache = _UploadCache()
+
+
 def _dev(a):
+    """Device copy of a host array (contiguous); large inputs go through the content cache."""
+    return _cache.get(a)
+
+
+def _dev_out(a):
+    """Device copy of an array the kernel will WRITE to (never shared with the cache)."""
     torch = _lib.require_cuda()
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
@@ -73,7 +139,7 @@ def find_positions(NO1, nz, fz1, p1s, fzGrid):
         return
     if fz1.size < NO1 or p1s.size < NO1 or fzGrid.size < nz:
         raise ValueError("array shapes are inconsistent with NO1=%d nz=%d" % (NO1, nz))
-    d_f, d_p, d_g = _dev(fz1[:NO1]), _dev(p1s[:NO1]), _dev(fzGrid[:nz])
+    d_f, d_p, d_g = _dev(fz1[:NO1]), _dev_out(p1s[:NO1]), _dev(fzGrid[:nz])
     _lib.check(_lib.lib().dl_find_positions_dev(NO1, nz, _lib.ptr(d_f), _lib.ptr(d_p),
                                                _lib.ptr(d_g), _lib.stream_ptr()))
     p1s[:NO1] = d_p.cpu().numpy()

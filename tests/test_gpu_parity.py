@@ -1093,3 +1093,35 @@ def test_fused_config5_shaped_slice_vs_compiled_reference():
         solid = ev[idx] > 1e-250 * ev[idx[0]]
         np.testing.assert_array_equal(res["top_idx"][o][solid], idx[solid])
         np.testing.assert_allclose(res["top_ev"][o][solid], ev[idx][solid], rtol=RTOL)
+
+
+def test_dropin_upload_cache_follows_content(orc):
+    """Drop-in mode re-uses the device copy of a big input when the caller hands over the same
+    CONTENT again (delight-apply.py:141-142 passes a fresh fancy-indexed copy of the model grid
+    per target), and never when the content changed -- even by one element, in place."""
+    from delight_b200 import utils_cy
+    from delight_b200.utils_cy import approx_flux_likelihood_cy
+    rng = np.random.default_rng(3)
+    nz, nt, nf = 300, 120, 5                       # 1.44 MB per array: above the cache threshold
+    f_mod = rng.uniform(0.5, 2, (nz, nt, nf)) * 1e5
+    f_cov = (f_mod * 0.01) ** 2
+    f_obs = f_mod[100, 7] * 4e-10
+    f_var = (0.05 * f_obs) ** 2
+    eh, ev = np.ones(nz), np.full(nz, 0.25)
+    utils_cy._cache.clear()
+    h0, m0 = utils_cy._cache.hits, utils_cy._cache.misses
+    a = np.zeros((nz, nt))
+    approx_flux_likelihood_cy(a, nz, nt, nf, f_obs, f_var, f_mod, f_cov, ell_hat=eh, ell_var=ev)
+    b = np.zeros((nz, nt))
+    approx_flux_likelihood_cy(b, nz, nt, nf, f_obs, f_var, f_mod[:, :, np.arange(nf)],
+                              f_cov[:, :, np.arange(nf)], ell_hat=eh, ell_var=ev)
+    assert utils_cy._cache.misses - m0 == 2 and utils_cy._cache.hits - h0 == 2
+    np.testing.assert_array_equal(a, b)
+    f_mod[100, 7, 2] *= 1.5                        # in-place change of one element
+    c = np.zeros((nz, nt))
+    approx_flux_likelihood_cy(c, nz, nt, nf, f_obs, f_var, f_mod, f_cov, ell_hat=eh, ell_var=ev)
+    assert utils_cy._cache.misses - m0 == 3
+    want = np.zeros((nz, nt))
+    orc.approx_flux_likelihood_cy(want, nz, nt, nf, f_obs, f_var, f_mod, f_cov, eh, ev)
+    np.testing.assert_allclose(c, want, rtol=RTOL, atol=1e-300)
+    assert not np.array_equal(a, c)
