@@ -1,8 +1,7 @@
 // Non-fused likelihood: the drop-in for delight/utils_cy.pyx:83-128 (one target per call, the
 // full like[nz][nt] array is returned in the reference's layout).  HBM-bound by construction:
-// 2*nf*8 B read + 8 B written per cell, so the literal formulas (divisions, logs) are kept and
-// the kernel is organised for coalescing only: one thread per (z, t) cell, nf contiguous
-// doubles per thread, cells contiguous across the warp.
+// 2*nf*8 B read + 8 B written per cell (+ 16 B for the exp pass): one thread per (z, t) cell,
+// nf contiguous doubles per thread, cells contiguous across the warp.
 #include "common.cuh"
 
 namespace dl {
@@ -16,40 +15,69 @@ __device__ __forceinline__ double dkey_inv(unsigned long long k) {
     return __longlong_as_double((long long)b);
 }
 
-// log-likelihood per cell (utils_cy.pyx:98-118) + global max (:120-124) via ordered atomicMax
+// log-likelihood per cell (utils_cy.pyx:98-118) + global max (:120-124) via ordered atomicMax.
+// The formulas are the reference's, evaluated with one IEEE reciprocal per band and pass (the
+// literal code divides three times by the same variance) and ONE log per cell: the product of
+// the variances is carried as mantissa x 2^exponent (renormalised every four bands, so any nf
+// and any unit system stay in range) instead of nf + 2 logs.  That keeps the kernel on the HBM
+// roofline (2 nf 8 B read + 8 B written per cell) instead of the FP64 pipe.
 __global__ void __launch_bounds__(256) loglike_kernel(
     long long ncell, int nt, int nf, const double* __restrict__ f_obs,
     const double* __restrict__ f_obs_var, const double* __restrict__ f_mod,
     const double* __restrict__ f_mod_covar, const double* __restrict__ ell_hat,
     const double* __restrict__ ell_var, double* __restrict__ like,
     unsigned long long* __restrict__ maxkey) {
-    extern __shared__ double sh[];                 // f_obs[nf], f_obs_var[nf]
-    for (int i = threadIdx.x; i < nf; i += blockDim.x) { sh[i] = f_obs[i]; sh[nf + i] = f_obs_var[i]; }
+    extern __shared__ double sh[];                 // f_obs[nf], f_obs_var[nf], f_obs^2[nf]
+    for (int i = threadIdx.x; i < nf; i += blockDim.x) {
+        sh[i] = f_obs[i]; sh[nf + i] = f_obs_var[i]; sh[2 * nf + i] = f_obs[i] * f_obs[i];
+    }
     __syncthreads();
+    const double LN2 = 0.693147180559945309417, LOG_2PI = 1.83787706640934548356;
     double best = -INFINITY;
     for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < ncell;
          cell += (long long)gridDim.x * blockDim.x) {
         const long long iz = cell / nt;
         const double eh = ell_hat[iz], ev = ell_var[iz];
+        const double iev = 1.0 / ev;
         const double* m = f_mod + cell * nf;
         const double* c = f_mod_covar + cell * nf;
-        double ell = 0.0, fot = 0.0, ftt = 0.0, foo = 0.0, logden = 0.0;
+        double ell2 = 0.0, fot = 0.0, ftt = 0.0, foo = 0.0, prod = 1.0;
+        int pexp = 0;
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
-            fot = eh / ev; ftt = 1.0 / ev; foo = eh * eh / ev; logden = 0.0;
+            fot = eh * iev; ftt = iev; foo = eh * eh * iev; prod = 1.0; pexp = 0;
             for (int k = 0; k < nf; ++k) {
                 const double mk = m[k];
-                const double var = sh[nf + k] + ell * ell * c[k];
-                fot += mk * sh[k] / var;
-                ftt += mk * mk / var;
-                foo += sh[k] * sh[k] / var;
-                if (pass == 1) logden += log(var * DL_TWO_PI);
+                const double var = fma(ell2, c[k], sh[nf + k]);          // :107
+                const double r = __drcp_rn(var);
+                const double mr = mk * r;
+                fot = fma(mr, sh[k], fot);                               // :108
+                ftt = fma(mr, mk, ftt);                                  // :109
+                foo = fma(sh[2 * nf + k], r, foo);                       // :110
+                if (pass == 1) {                                         // :111-112
+                    prod *= var;
+                    if ((k & 3) == 3) {
+                        const int e = ilogb(prod);
+                        if (e > -1000 && e < 1000) { prod = scalbn(prod, -e); pexp += e; }
+                    }
+                }
             }
-            ell = fot / ftt;
+            const double ell = fot / ftt;                                // :113
+            ell2 = ell * ell;
         }
-        const double chi2 = foo - fot * fot / ftt;
-        logden += log(DL_TWO_PI * ev) + log(ftt / DL_TWO_PI);
-        const double L = -0.5 * chi2 - 0.5 * logden;
+        const double chi2 = foo - fot * fot / ftt;                       // :115
+        // logDenom = sum log(2 pi var) + log(2 pi ell_var) + log(FTT / 2 pi)     (:111-117)
+        double logden;
+        {
+            int e = ilogb(prod);
+            if (e > -1000 && e < 1000) { prod = scalbn(prod, -e); pexp += e; }
+            const double t = ev * ftt;                                   // > 0
+            e = ilogb(t);
+            double tm = t;
+            if (e > -1000 && e < 1000) { tm = scalbn(t, -e); pexp += e; }
+            logden = log(prod * tm) + pexp * LN2 + nf * LOG_2PI;
+        }
+        const double L = -0.5 * chi2 - 0.5 * logden;                     // :118
         like[cell] = L;
         best = fmax(best, L);
     }
@@ -97,7 +125,7 @@ int dl_approx_flux_likelihood_dev(double* like, long long nz, long long nt, long
     DL_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     long long blocks = (ncell + 255) / 256;
     if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;   // grid-stride, 16 CTAs/SM
-    loglike_kernel<<<(unsigned)blocks, 256, 2 * nf * sizeof(double), stream>>>(
+    loglike_kernel<<<(unsigned)blocks, 256, 3 * nf * sizeof(double), stream>>>(
         ncell, (int)nt, (int)nf, f_obs, f_obs_var, f_mod, f_mod_covar, ell_hat, ell_var, like,
         (unsigned long long*)scratch);
     DL_CUDA_CHECK(cudaGetLastError());

@@ -23,3 +23,10 @@ $LIST > gpurun_out/${TAG}_plain_list.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file gpurun_out/${TAG}_launches.csv $LIST > gpurun_out/${TAG}_ncu_list.log 2>&1
 tail -2 gpurun_out/${TAG}_plain_full.log
+# 4. the other kernels (subsystems 2 and 3, drop-in operator, epilogue): selected counters
+SMALLK="python tools/prof_small.py"
+$SMALLK > gpurun_out/${TAG}_plain_smallk.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__throughput.avg.pct_of_peak_sustained_elapsed,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,launch__grid_size,launch__block_size \
+    --clock-control none -k regex:'kernel_grid|kernelparts|gp_fit|gp_predict|topk|loglike|expnorm|compressed|metrics_kernel|ci_levels|finalize|prep_targets|anchor|zprior|relayout' \
+    --csv --log-file gpurun_out/${TAG}_small_kernels.csv $SMALLK > gpurun_out/${TAG}_ncu_smallk.log 2>&1
+cat gpurun_out/${TAG}_plain_smallk.log
