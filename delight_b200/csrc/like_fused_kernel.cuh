@@ -40,7 +40,11 @@ namespace dl {
 
 constexpr int FTO = 4;        // targets per warp
 constexpr int MAXNF = 32;     // bands per target
-constexpr int REGNF = 8;      // up to here the model values of a z-group are cached in registers
+#ifndef DL_REGNF
+#define DL_REGNF 7
+#endif
+constexpr int REGNF = DL_REGNF;   // up to here the model values of a z-group are cached in registers
+constexpr int BIGNF = 8;      // beyond: band loops partially rolled, determinant in two factors
 constexpr int ZJ = 2;         // redshifts a lane processes jointly (independent dependency chains)
 #ifndef DL_STAGES
 #define DL_STAGES 4
@@ -54,12 +58,24 @@ constexpr int ZJ = 2;         // redshifts a lane processes jointly (independent
 #ifndef DL_CHI2_EARLY
 #define DL_CHI2_EARLY 0
 #endif
+#ifndef DL_BAND_UNROLL0
+#define DL_BAND_UNROLL0 4     // pass-0 band loop beyond REGNF bands
+#endif
+#ifndef DL_BAND_UNROLL1
+#define DL_BAND_UNROLL1 2     // pass-1 band-pair loop beyond REGNF bands
+#endif
+#ifndef DL_TAILPAIR
+#define DL_TAILPAIR 2
+#endif
 #ifndef DL_TJ2_NF
-#define DL_TJ2_NF 17
+#define DL_TJ2_NF 8
 #endif
 #ifndef DL_CFG1_NF
 #define DL_CFG1_NF 9          // homogeneous band sets from here on use config 1
 #endif
+
+constexpr int BAND_UNROLL0 = DL_BAND_UNROLL0;   // (macros are not expanded inside #pragma unroll)
+constexpr int BAND_UNROLL1 = DL_BAND_UNROLL1;
 
 enum { MODE_MAIN = 0, MODE_SAMPLE = 1 };
 
@@ -162,7 +178,12 @@ __device__ __forceinline__ void cells_xy(const double* const (&tcs)[TJ], const M
     for (int j = 0; j < TJ; ++j)
 #pragma unroll
         for (int c = 0; c < ZJ; ++c) { fot[j][c] = pOT0[j][c]; ftt[j][c] = pTT[j][c]; }
-#pragma unroll
+    // (band loops: fully unrolled with the model in registers -- the register arrays need
+    // static indices; partially unrolled beyond REGNF bands, where full unrolling lets the
+    // compiler hoist the loads of all bands and spill: 21 bands, two targets jointly: 25 LDL +
+    // 21 STL per 64 cells and 16 % long-scoreboard stalls, profiles/r2_fused_nf21_ncu_summary.txt)
+    constexpr bool ROLL = NF > BIGNF;
+#pragma unroll (ROLL ? BAND_UNROLL0 : NF)
     for (int f = 0; f < NF; ++f) {
         double mf[ZJ];
 #pragma unroll
@@ -198,8 +219,9 @@ __device__ __forceinline__ void cells_xy(const double* const (&tcs)[TJ], const M
         foo[j][c] = fma(tc2[j][f], r, foo[j][c]);
     };
     constexpr int NG = (NF / 2) * 2;
-#pragma unroll
-    for (int f = 0; f < NG; f += 2) {
+    // beyond REGNF bands the determinant is carried as two factors (pairs from F0 on go to P2)
+    constexpr int F0 = ROLL ? ((NF / 2 + 1) & ~1) : NG;
+    auto pair = [&](int f, double (&Pd)[TJ][ZJ]) {
         double ma[ZJ], mb[ZJ], ca[ZJ], cb[ZJ];
 #pragma unroll
         for (int c = 0; c < ZJ; ++c) {
@@ -217,10 +239,14 @@ __device__ __forceinline__ void cells_xy(const double* const (&tcs)[TJ], const M
                 const double ri = rcp_fast(pab);
                 acc(j, c, f, ma[c], vb * ri, voa.y);
                 acc(j, c, f + 1, mb[c], va * ri, vob.y);
-                if (NF > REGNF && f >= NF / 2) P2[j][c] *= pab; else P[j][c] *= pab;
+                Pd[j][c] *= pab;
             }
         }
-    }
+    };
+#pragma unroll (ROLL ? BAND_UNROLL1 : NF)
+    for (int f = 0; f < F0; f += 2) pair(f, P);
+#pragma unroll (ROLL ? BAND_UNROLL1 : NF)
+    for (int f = F0; f < NG; f += 2) pair(f, P2);
     if (NF - NG == 1) {
         constexpr int f = NF - 1;
         double ma[ZJ], ca[ZJ];
@@ -233,7 +259,7 @@ __device__ __forceinline__ void cells_xy(const double* const (&tcs)[TJ], const M
             for (int c = 0; c < ZJ; ++c) {
                 const double var = fma(e2[j][c], ca[c], vo.x);
                 acc(j, c, f, ma[c], rcp_fast(var), vo.y);
-                if (NF > REGNF) P2[j][c] *= var; else P[j][c] *= var;
+                if (NF > BIGNF) P2[j][c] *= var; else P[j][c] *= var;
             }
         }
     }
@@ -244,7 +270,7 @@ __device__ __forceinline__ void cells_xy(const double* const (&tcs)[TJ], const M
 #pragma unroll
         for (int c = 0; c < ZJ; ++c) {
             double rF;
-            if (NF > REGNF) {
+            if (NF > BIGNF) {
                 // many bands: the determinant is kept as two factors so that it cannot leave
                 // the double range (model variance >> observed variance in every band), and
                 // 1/FTT has its own reciprocal
@@ -282,6 +308,11 @@ fused_like_kernel(const FusedParams p) {
     // two targets: 13 bands 77.3 / 79.9 ms, 16: 92.5 / 98.3, 21: 131.6 / 126.5, 28: 178.5 / 173.1)
     constexpr int TJ = (SMODEL && !HET && NF >= DL_TJ2_NF) ? 2 : 1;
     static_assert(FTO % TJ == 0, "TJ must divide the targets of a warp");
+    // targets whose TAILS (exp, max tracking, accumulation) are evaluated together: the tail of
+    // a cell is one long dependent chain, so with the model in registers (heads one target at a
+    // time) the tails of DL_TAILPAIR targets are interleaved
+    constexpr int TP = (!SMODEL && !SAMPLE && TJ < DL_TAILPAIR) ? DL_TAILPAIR : TJ;
+    static_assert(FTO % TP == 0 && TP % TJ == 0, "bad tail pairing");
     const int nU = HET ? p.nU : NF;
     const int ROWS = 2 * nU + 2 + (ZDEP ? 4 : 0);
     const int STG = p.stages;
@@ -471,85 +502,107 @@ fused_like_kernel(const FusedParams p) {
                 }
             }
 #pragma unroll (SMODEL || SAMPLE ? 1 : FTO)
-            for (int o = 0; o < FTO; o += TJ) {
-                // E[] is rotated once per target (group) so the loop can stay rolled with the
-                // accumulators in registers (FTO / TJ rotations restore the order)
-                double Eo[TJ];
-                const double* tcs[TJ];
-                double pOT0[TJ][ZJ], pOT[TJ][ZJ], pTT[TJ][ZJ], pOO[TJ][ZJ], xm[TJ][ZJ];
+            for (int o = 0; o < FTO; o += TP) {
+                // E[] is rotated once per target group so the loop can stay rolled with the
+                // accumulators in registers (FTO / TP rotations restore the order)
+                double Eo[TP];
+                double x[TP][ZJ], y[TP][ZJ];
 #pragma unroll
-                for (int j = 0; j < TJ; ++j) {
-                    Eo[j] = E[j];
-                    tcs[j] = tcw + (o + j) * TCS;
-                    const double* tk = tcs[j] + 5 * NF;
+                for (int j = 0; j < TP; ++j) Eo[j] = E[j];
+                // heads: x = -chi2/2 - A and y = det^-1/2, TJ targets at a time
 #pragma unroll
-                    for (int c = 0; c < ZJ; ++c) {
-                        if (ZDEP) {
-                            const double cc = tk[TC_C];
-                            pOT0[j][c] = tk[TC_CS] * zot[c];
-                            pOT[j][c] = cc * zot[c]; pTT[j][c] = cc * ztt[c];
-                            pOO[j][c] = cc * zoo[c];
-                            xm[j][c] = SAMPLE ? xmask[c] : xmask[c] + tk[TC_XOFF];     // -A
-                        } else {
-                            // the anchor is folded into the constant term of FOO (TC_POO); the
-                            // sampling pass measures the un-anchored exponent (TC_POO0)
-                            pOT0[j][c] = tk[TC_POT0];
-                            pOT[j][c] = tk[TC_POT]; pTT[j][c] = tk[TC_PTT];
-                            pOO[j][c] = tk[SAMPLE ? TC_POO0 : TC_POO];
-                            xm[j][c] = xmask[c];
+                for (int g = 0; g < TP; g += TJ) {
+                    const double* tcs[TJ];
+                    double pOT0[TJ][ZJ], pOT[TJ][ZJ], pTT[TJ][ZJ], pOO[TJ][ZJ], xm[TJ][ZJ];
+                    double xg[TJ][ZJ], yg[TJ][ZJ];
+#pragma unroll
+                    for (int j = 0; j < TJ; ++j) {
+                        tcs[j] = tcw + (o + g + j) * TCS;
+                        const double* tk = tcs[j] + 5 * NF;
+#pragma unroll
+                        for (int c = 0; c < ZJ; ++c) {
+                            if (ZDEP) {
+                                const double cc = tk[TC_C];
+                                pOT0[j][c] = tk[TC_CS] * zot[c];
+                                pOT[j][c] = cc * zot[c]; pTT[j][c] = cc * ztt[c];
+                                pOO[j][c] = cc * zoo[c];
+                                xm[j][c] = SAMPLE ? xmask[c] : xmask[c] + tk[TC_XOFF];   // -A
+                            } else {
+                                // the anchor is folded into the constant term of FOO (TC_POO);
+                                // the sampling pass measures the un-anchored exponent (TC_POO0)
+                                pOT0[j][c] = tk[TC_POT0];
+                                pOT[j][c] = tk[TC_POT]; pTT[j][c] = tk[TC_PTT];
+                                pOO[j][c] = tk[SAMPLE ? TC_POO0 : TC_POO];
+                                xm[j][c] = xmask[c];
+                            }
                         }
                     }
-                }
-                double x[TJ][ZJ], y[TJ][ZJ];
-                if constexpr (HET)
-                    cells_xy<NF, TJ>(tcs, SmemModelHet<NF, FZC>{st + zl,
-                                         reinterpret_cast<const int*>(tcs[0] + 5 * NF + TC_NCONST),
-                                         var0},
-                                     pOT0, pOT, pTT, pOO, zev, xm, x, y);
-                else if constexpr (SMODEL)
-                    cells_xy<NF, TJ>(tcs, SmemModel<NF, FZC>{st + zl}, pOT0, pOT, pTT, pOO, zev,
-                                     xm, x, y);
-                else
-                    cells_xy<NF, TJ>(tcs, RegModel<NF>{m, cv}, pOT0, pOT, pTT, pOO, zev, xm, x, y);
+                    if constexpr (HET)
+                        cells_xy<NF, TJ>(tcs, SmemModelHet<NF, FZC>{st + zl,
+                                             reinterpret_cast<const int*>(tcs[0] + 5 * NF + TC_NCONST),
+                                             var0},
+                                         pOT0, pOT, pTT, pOO, zev, xm, xg, yg);
+                    else if constexpr (SMODEL)
+                        cells_xy<NF, TJ>(tcs, SmemModel<NF, FZC>{st + zl}, pOT0, pOT, pTT, pOO,
+                                         zev, xm, xg, yg);
+                    else
+                        cells_xy<NF, TJ>(tcs, RegModel<NF>{m, cv}, pOT0, pOT, pTT, pOO, zev, xm,
+                                         xg, yg);
 #pragma unroll
-                for (int j = 0; j < TJ; ++j) {
-                    if constexpr (SAMPLE) {
+                    for (int j = 0; j < TJ; ++j)
+#pragma unroll
+                        for (int c = 0; c < ZJ; ++c) { x[g + j][c] = xg[j][c]; y[g + j][c] = yg[j][c]; }
+                }
+                // tails of the TP targets together: the exp chains are long and dependent, so
+                // they are interleaved (TP x ZJ independent chains) before the first branch
+                if constexpr (SAMPLE) {
+#pragma unroll
+                    for (int j = 0; j < TP; ++j) {
                         double xl = x[j][0];
 #pragma unroll
                         for (int c = 1; c < ZJ; ++c) xl = fmax(xl, x[j][c]);
                         Eo[j] = fmax(Eo[j], xl);
-                    } else {
-                        double v[ZJ];
-                        int vh = 0;
+                    }
+                } else {
+                    double v[TP][ZJ];
+                    int vh[TP];
+#pragma unroll
+                    for (int j = 0; j < TP; ++j) {
+                        vh[j] = 0;
 #pragma unroll
                         for (int c = 0; c < ZJ; ++c) {
-                            v[c] = exp_nonpos_tab(x[j][c], etab) * y[j][c];      // :118,128
+                            v[j][c] = exp_nonpos_tab(x[j][c], etab) * y[j][c];      // :118,128
                             ovf = max(ovf, __double2hiint(x[j][c]));
-                            vh = max(vh, __double2hiint(v[c]));
+                            vh[j] = max(vh[j], __double2hiint(v[j][c]));
                         }
+                    }
+#pragma unroll
+                    for (int j = 0; j < TP; ++j) {
                         // running max of v (the final divisor), kept per target in shared
                         // memory: only the high word is read here; the rare record-breaking
                         // cells take the slow path (O(log) times per lane)
                         unsigned long long* Vt = V_sm + tfirst + o + j;
-                        if (vh >= reinterpret_cast<const int*>(Vt)[1]) {
+                        if (vh[j] >= reinterpret_cast<const int*>(Vt)[1]) {
 #pragma unroll
                             for (int c = 0; c < ZJ; ++c)
-                                if (v[c] == v[c])
-                                    atomicMax(Vt, (unsigned long long)__double_as_longlong(v[c]));
+                                if (v[j][c] == v[j][c])
+                                    atomicMax(Vt, (unsigned long long)__double_as_longlong(v[j][c]));
                         }
-                        // prior, PDF and evidence accumulation  (delight-apply.py:145-148)
+                    }
+                    // prior, PDF and evidence accumulation  (delight-apply.py:145-148)
+#pragma unroll
+                    for (int j = 0; j < TP; ++j)
 #pragma unroll
                         for (int c = 0; c < ZJ; ++c) {
-                            const double vp = v[c] * pr[c];
+                            const double vp = v[j][c] * pr[c];
                             pdfw[(o + j) * FZC + zl + 32 * c] += vp;
                             Eo[j] = fma(vp, wzv[c], Eo[j]);
                         }
-                    }
                 }
 #pragma unroll
-                for (int q = 0; q + TJ < FTO; ++q) E[q] = E[q + TJ];
+                for (int q = 0; q + TP < FTO; ++q) E[q] = E[q + TP];
 #pragma unroll
-                for (int j = 0; j < TJ; ++j) E[FTO - TJ + j] = Eo[j];
+                for (int j = 0; j < TP; ++j) E[FTO - TP + j] = Eo[j];
             }
         }
         if constexpr (!SAMPLE) {
