@@ -64,6 +64,9 @@ constexpr int ZJ = 2;         // redshifts a lane processes jointly (independent
 #ifndef DL_BAND_UNROLL1
 #define DL_BAND_UNROLL1 2     // pass-1 band-pair loop beyond REGNF bands
 #endif
+#ifndef DL_HYBRID
+#define DL_HYBRID 0
+#endif
 #ifndef DL_TAILPAIR
 #define DL_TAILPAIR 2
 #endif
@@ -138,6 +141,15 @@ struct RegModel {
     const double (&cc)[ZJ][NF];
     __device__ __forceinline__ double m(int c, int f) const { return mm[c][f]; }
     __device__ __forceinline__ double cv(int c, int f) const { return cc[c][f]; }
+};
+// band means in registers, band variances read from the stage: half the register footprint of
+// RegModel, which makes room for two targets jointly (DL_HYBRID)
+template <int NF, int FZC>
+struct HybridModel {
+    const double (&mm)[ZJ][NF];
+    const double* stz;      // stage + the lane's first redshift
+    __device__ __forceinline__ double m(int c, int f) const { return mm[c][f]; }
+    __device__ __forceinline__ double cv(int c, int f) const { return stz[(NF + f) * FZC + 32 * c]; }
 };
 template <int NF, int FZC>
 struct SmemModel {
@@ -306,7 +318,8 @@ fused_like_kernel(const FusedParams p) {
     // targets evaluated jointly: two from DL_TJ2_NF bands on, where the model values are read from
     // the stage for every use and sharing them pays (measured, 2048 x 1500 x 1500 cells, one vs
     // two targets: 13 bands 77.3 / 79.9 ms, 16: 92.5 / 98.3, 21: 131.6 / 126.5, 28: 178.5 / 173.1)
-    constexpr int TJ = (SMODEL && !HET && NF >= DL_TJ2_NF) ? 2 : 1;
+    constexpr bool HYBRID = DL_HYBRID && !SMODEL;     // means in registers, variances from the stage
+    constexpr int TJ = ((SMODEL && !HET && NF >= DL_TJ2_NF) || HYBRID) ? 2 : 1;
     static_assert(FTO % TJ == 0, "TJ must divide the targets of a warp");
     // targets whose TAILS (exp, max tracking, accumulation) are evaluated together: the tail of
     // a cell is one long dependent chain, so with the model in registers (heads one target at a
@@ -484,7 +497,7 @@ fused_like_kernel(const FusedParams p) {
 #pragma unroll
                     for (int c = 0; c < ZJ; ++c) {
                         m[c][f] = st[f * FZC + zl + 32 * c];
-                        cv[c][f] = st[(NF + f) * FZC + zl + 32 * c];
+                        if (!HYBRID) cv[c][f] = st[(NF + f) * FZC + zl + 32 * c];
                     }
                 }
             }
@@ -544,6 +557,9 @@ fused_like_kernel(const FusedParams p) {
                                          pOT0, pOT, pTT, pOO, zev, xm, xg, yg);
                     else if constexpr (SMODEL)
                         cells_xy<NF, TJ>(tcs, SmemModel<NF, FZC>{st + zl}, pOT0, pOT, pTT, pOO,
+                                         zev, xm, xg, yg);
+                    else if constexpr (HYBRID)
+                        cells_xy<NF, TJ>(tcs, HybridModel<NF, FZC>{m, st + zl}, pOT0, pOT, pTT, pOO,
                                          zev, xm, xg, yg);
                     else
                         cells_xy<NF, TJ>(tcs, RegModel<NF>{m, cv}, pOT0, pOT, pTT, pOO, zev, xm,

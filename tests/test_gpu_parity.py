@@ -1125,3 +1125,89 @@ def test_dropin_upload_cache_follows_content(orc):
     orc.approx_flux_likelihood_cy(want, nz, nt, nf, f_obs, f_var, f_mod, f_cov, eh, ev)
     np.testing.assert_allclose(c, want, rtol=RTOL, atol=1e-300)
     assert not np.array_equal(a, c)
+
+
+def test_host_abi_of_the_kernel_operators(orc):
+    """The raw C ABI with HOST pointers (what a foreign-function binding of
+    delight.photoz_kernels_cy / delight.utils_cy binds, include/delight_b200.h) for kernelparts,
+    kernelparts_diag, find_positions and kernel_parts_interp, against the oracle -- including the
+    accumulate-then-normalise contract of kernelparts on non-zero output buffers and the error
+    code for an out-of-range band index."""
+    from delight_b200 import _lib
+    L = _lib.lib()
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rng = np.random.default_rng(17)
+    NO1, NO2, nB, NC, NL = 19, 7, 4, 7, 3
+    amp = rng.uniform(0.1, 1, (nB, NC))
+    mu = rng.uniform(3000, 9000, (nB, 1)) + rng.uniform(-400, 400, (nB, NC))
+    sig = rng.uniform(50, 300, (nB, NC))
+    norms = np.sqrt(2 * np.pi) * np.sum(amp * sig, axis=1)
+    lines = rng.uniform(3000, 7000, NL)
+    b1, b2 = rng.integers(0, nB, NO1), rng.integers(0, nB, NO2)
+    fz1, fz2 = 1 + rng.uniform(0, 3, NO1), 1 + rng.uniform(0, 3, NO2)
+    want = [rng.uniform(0, 1e-3, (NO1, NO2)) for _ in range(5)]
+    got = [w.copy() for w in want]
+    orc.kernelparts(NO1, NO2, NC, NL, 1e3, 1e2, amp, mu, sig, lines, np.full(NL, 20.0), norms,
+                    b1, fz1, b2, fz2, True, *want)
+    _lib.check(L.dl_kernelparts_host(NO1, NO2, NC, NL, 1e3, 1e2, nB, P(amp), P(mu), P(sig),
+                                     P(lines), P(norms), P(b1), P(fz1), P(b2), P(fz2), 1,
+                                     *[P(g) for g in got]))
+    for k, (g_, w_) in enumerate(zip(got, want)):
+        np.testing.assert_allclose(g_, w_, rtol=RTOL,
+                                   atol=1e-12 * np.abs(w_).max() if k == 4 else 1e-300)
+    wd = [np.zeros(NO1) for _ in range(4)]
+    gd = [np.zeros(NO1) for _ in range(4)]
+    orc.kernelparts_diag(NO1, NC, NL, 1e3, 1e2, amp, mu, sig, lines, np.full(NL, 20.0), norms,
+                         b1, fz1, True, *wd)
+    _lib.check(L.dl_kernelparts_diag_host(NO1, NC, NL, 1e3, 1e2, nB, P(amp), P(mu), P(sig),
+                                          P(lines), P(norms), P(b1), P(fz1), 1,
+                                          *[P(g) for g in gd]))
+    for g_, w_ in zip(gd, wd):
+        np.testing.assert_allclose(g_, w_, rtol=RTOL, atol=1e-300)
+    bad = b1.copy()
+    bad[3] = nB
+    assert L.dl_kernelparts_diag_host(NO1, NC, NL, 1e3, 1e2, nB, P(amp), P(mu), P(sig), P(lines),
+                                      P(norms), P(bad), P(fz1), 1, *[P(g) for g in gd]) != 0
+    assert b"band" in L.dl_last_error()
+    # find_positions + kernel_parts_interp
+    nzg = 13
+    fzg = 1 + np.logspace(np.log10(0.01), np.log10(3.03), nzg)
+    x1 = np.concatenate([rng.uniform(fzg[0], fzg[-1], NO1 - 2), [fzg[0] - 0.1, fzg[-1] + 1.0]])
+    x2 = rng.uniform(fzg[0], fzg[-1], NO2)
+    p1w, p1g = np.full(NO1, 5, dtype=np.int64), np.full(NO1, 5, dtype=np.int64)
+    orc.find_positions(NO1, nzg, x1, p1w, fzg)
+    _lib.check(L.dl_find_positions_host(NO1, nzg, P(x1), P(p1g), P(fzg)))
+    np.testing.assert_array_equal(p1g, p1w)
+    assert p1g[-1] == 5 and p1g[-2] == 5                  # outside the grid: left untouched
+    p2 = np.zeros(NO2, dtype=np.int64)
+    orc.find_positions(NO2, nzg, x2, p2, fzg)
+    Kgrid = rng.uniform(0, 1, (nB, nB, nzg, nzg))
+    kw, kg = np.zeros((NO1, NO2)), np.zeros((NO1, NO2))
+    p1 = np.clip(p1w, 0, nzg - 2)
+    orc.kernel_parts_interp(NO1, NO2, kw, b1, x1, p1, b2, x2, p2, fzg, Kgrid)
+    _lib.check(L.dl_kernel_parts_interp_host(NO1, NO2, P(kg), P(b1), P(x1), P(p1), P(b2), P(x2),
+                                             P(p2), P(fzg), P(Kgrid), nB, nzg))
+    np.testing.assert_allclose(kg, kw, rtol=RTOL, atol=1e-300)
+
+
+def test_dropin_nan_cell_is_local_like_the_reference(orc):
+    """A NaN model cell that is NOT cell (0, 0): the reference's max scan skips it
+    (utils_cy.pyx:120-124 compares with `>`) and only that cell of the output is NaN.  Same here.
+    (A NaN in cell (0, 0) turns the reference's whole output into NaN; the CUDA operator still
+    skips it -- the documented divergence of DESIGN section 2.)"""
+    from delight_b200.utils_cy import approx_flux_likelihood_cy
+    rng = np.random.default_rng(8)
+    nz, nt, nf = 9, 11, 3
+    f_obs, f_var = rng.uniform(1, 2, nf), rng.uniform(.1, .2, nf)
+    f_mod = rng.uniform(1, 2, (nz, nt, nf))
+    f_cov = rng.uniform(.1, .2, (nz, nt, nf))
+    f_mod[4, 6, 1] = np.nan
+    eh, ev = np.ones(nz), np.full(nz, .25)
+    want, got = np.zeros((nz, nt)), np.zeros((nz, nt))
+    orc.approx_flux_likelihood_cy(want, nz, nt, nf, f_obs, f_var, f_mod, f_cov, eh, ev)
+    approx_flux_likelihood_cy(got, nz, nt, nf, f_obs, f_var, f_mod, f_cov, ell_hat=eh, ell_var=ev)
+    assert np.isnan(got[4, 6]) and np.isnan(want[4, 6])
+    ok = ~np.isnan(want)
+    assert ok.sum() == nz * nt - 1
+    np.testing.assert_allclose(got[ok], want[ok], rtol=RTOL)
+    assert got[ok].max() == 1.0
