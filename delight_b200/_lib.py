@@ -57,16 +57,18 @@ _SIGS = {
     "dl_gp_fit_dev": [c_ll, c_ll, c_ll, c_ll, c_ll, c_p, c_p, c_p, c_p, c_p, c_p, c_d, c_d, c_p,
                       c_p, c_p, c_p, c_p, c_p, c_ll, c_p],
     "dl_gp_predict_dev": [c_ll, c_ll, c_ll, c_ll, c_ll, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
-                          c_d, c_d, c_p, c_ll, c_p, c_p, c_p],
+                          c_d, c_d, c_p, c_ll, c_p, c_p, c_p, c_p],
+    "dl_gp_tables_bytes": [c_ll, c_ll],
+    "dl_gp_tables_dev": [c_ll, c_ll, c_p, c_p, c_p, c_p, c_p],
     "dl_gp_predict_at_dev": [c_ll, c_ll, c_ll, c_ll, c_ll, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
-                             c_d, c_d, c_p, c_ll, c_p, c_p, c_p],
+                             c_d, c_d, c_p, c_ll, c_p, c_p, c_p, c_p],
     "dl_launch_count": [],
     "dl_timing_enable": [c_i],
     "dl_timing_collect": [c_p, c_p],
     "dl_fp64_peak": [c_i, c_p],
     "dl_selftest_math_dev": [c_ll, c_p, c_p, c_p],
 }
-_RESTYPES = {"dl_fused_padded_nz": c_ll, "dl_launch_count": c_ll, "dl_fused_workspace_bytes": c_ll,
+_RESTYPES = {"dl_fused_padded_nz": c_ll, "dl_gp_tables_bytes": c_ll, "dl_launch_count": c_ll, "dl_fused_workspace_bytes": c_ll,
              "dl_last_error": ctypes.c_char_p}
 
 EXPORTED = sorted(list(_SIGS) + ["dl_last_error"])

@@ -31,6 +31,11 @@ struct GPModel {
     const double* zgrid;   // [nz]    fine redshift grid
     int nB, nzg, nt, nz;
     double V_C, V_L;
+    // galaxy-independent tables of dl_gp_tables_dev (NULL: recomputed per galaxy)
+    const double* dls_tab;  // [nzg]  approx_DL(zGP)
+    const int* p1_tab;      // [nzg]  find_pos(fzGrid, 1 + zGP)
+    const int* tlo_tab;     // [nzg]  bin_left(zgrid, zGP)      (template tables)
+    const int* flo_tab;     // [nz]   bin_left(zGP, zgrid)      (coarse -> fine interpolation)
 };
 
 // delight/utils.py:12-13
@@ -247,20 +252,31 @@ __global__ void __launch_bounds__(PRED_THREADS) gp_predict_kernel(
     const double fz = 1.0 + z;
     const double dlz = approx_DL(z);
     const int p2 = s_p2, best = s_best;
+    // galaxy-side half of the bilinear weights (photoz_kernels_cy.pyx:25-35), once per galaxy
+    const double yl = gm.fzGrid[p2], yh = gm.fzGrid[p2 + 1];
+    const double wyl = yh - fz, wyh = fz - yl, dy = yh - yl;
     for (int node = tid; node < nB * nzg; node += PRED_THREADS) {
         const int bs = node / nzg, iz = node % nzg;
         const double zs = gm.zGP[iz];
         const double xs = 1.0 + zs;
-        const int p1 = find_pos(gm.fzGrid, nzg, xs);
-        const double dls = approx_DL(zs);
+        const int p1 = gm.p1_tab ? gm.p1_tab[iz] : find_pos(gm.fzGrid, nzg, xs);
+        const double dls = gm.dls_tab ? gm.dls_tab[iz] : approx_DL(zs);
         // Zprefac (photoz_kernels.py:338-340), g_AB = 1
         const double zp = (1.0 + zs) * (1.0 + z) / (4.0 * M_PI * 1.0 * dls * dlz);
         const double pref = zp * zp * ell * ell;
+        // node-side half of the bilinear weights; same operation order as bilin()
+        const double xl = gm.fzGrid[p1], xh = gm.fzGrid[p1 + 1];
+        const double inv = 1.0 / (xh - xl) / dy;
+        const double w00 = (xh - xs) * wyl, w10 = (xs - xl) * wyl;
+        const double w01 = (xh - xs) * wyh, w11 = (xs - xl) * wyh;
+        const size_t o00 = (size_t)p1 * nzg + p2, o10 = o00 + nzg;
         double acc = 0.0, q = 0.0;
         for (int j = 0; j < B; ++j) {
             const size_t g = ((size_t)bs * nB + s_band[j]) * nzg * nzg;
-            const double kc = bilin(gm.KCg + g, nzg, gm.fzGrid, p1, xs, p2, fz);
-            const double kl = bilin(gm.KLg + g, nzg, gm.fzGrid, p1, xs, p2, fz);
+            const double* C = gm.KCg + g;
+            const double* Lg = gm.KLg + g;
+            const double kc = inv * (w00 * C[o00] + w10 * C[o10] + w01 * C[o00 + 1] + w11 * C[o10 + 1]);
+            const double kl = inv * (w00 * Lg[o00] + w10 * Lg[o10] + w01 * Lg[o00 + 1] + w11 * Lg[o10 + 1]);
             const double kj = pref * (gm.V_C * kc + gm.V_L * kl);
             acc = fma(kj, beta[j], acc);
             double s = kj;          // forward substitution: w = L^-1 k ; k^T A^-1 k = |w|^2
@@ -276,7 +292,8 @@ __global__ void __launch_bounds__(PRED_THREADS) gp_predict_kernel(
                           (gm.V_C * gm.KCd[bs * nzg + iz] + gm.V_L * gm.KLd[bs * nzg + iz]);
         // mean function: ell * T[bestType, b*](z*)  (photoz_kernels.py:32-55)
         const double* tab = gm.tmpl + ((size_t)best * nB + bs) * nz;
-        const double mf = ell * lin_interp(gm.zgrid, tab, bin_left(gm.zgrid, nz, zs), zs);
+        const int tlo = gm.tlo_tab ? gm.tlo_tab[iz] : bin_left(gm.zgrid, nz, zs);
+        const double mf = ell * lin_interp(gm.zgrid, tab, tlo, zs);
         nmean[node] = acc + mf;
         nvar[node] = kd - q;
     }
@@ -298,13 +315,30 @@ __global__ void __launch_bounds__(PRED_THREADS) gp_predict_kernel(
         double mval = 0.0, vval = 0.0;       // padding: mean 0, model variance 0
         if (zf < nz) {
             const double zv = gm.zgrid[zf];
-            const int lo = bin_left(gm.zGP, nzg, zv);
+            const int lo = gm.flo_tab ? gm.flo_tab[zf] : bin_left(gm.zGP, nzg, zv);
             mval = lin_interp(gm.zGP, nmean + b * nzg, lo, zv);
             vval = lin_interp(gm.zGP, nvar + b * nzg, lo, zv);
         }
         g_mean[i] = mval;
         g_var[i] = vval;
     }
+}
+
+// galaxy-independent lookups of gp_predict_kernel, once per model: without them every galaxy
+// repeats 150 pow/exp calls and ~10k binary searches with dependent global loads
+__global__ void gp_tables_kernel(int nzg, int nz, const double* __restrict__ zGP,
+                                 const double* __restrict__ fzGrid,
+                                 const double* __restrict__ zgrid, double* __restrict__ dls,
+                                 int* __restrict__ p1, int* __restrict__ tlo,
+                                 int* __restrict__ flo) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nzg) {
+        const double zs = zGP[i];
+        dls[i] = approx_DL(zs);
+        p1[i] = find_pos(fzGrid, nzg, 1.0 + zs);
+        tlo[i] = bin_left(zgrid, nz, zs);
+    }
+    if (i < nz) flo[i] = bin_left(zGP, nzg, zgrid[i]);
 }
 
 }  // namespace dl
@@ -314,6 +348,40 @@ using namespace dl;
 extern "C" {
 
 long long dl_fused_padded_nz(long long nz);
+
+// bytes of the table buffer of dl_gp_tables_dev
+long long dl_gp_tables_bytes(long long nzg, long long nz) {
+    return ((nzg * 8 + 255) & ~255ll) + 3 * ((nzg * 4 + 255) & ~255ll) + ((nz * 4 + 255) & ~255ll);
+}
+
+static void gp_set_tables(GPModel& gm, const void* tables) {
+    gm.dls_tab = nullptr; gm.p1_tab = nullptr; gm.tlo_tab = nullptr; gm.flo_tab = nullptr;
+    if (!tables) return;
+    const char* w = (const char*)tables;
+    const size_t a8 = ((size_t)gm.nzg * 8 + 255) & ~(size_t)255, a4 = ((size_t)gm.nzg * 4 + 255) & ~(size_t)255;
+    gm.dls_tab = (const double*)w; w += a8;
+    gm.p1_tab = (const int*)w; w += a4;
+    gm.tlo_tab = (const int*)w; w += a4;
+    w += a4;                                   // (spare)
+    gm.flo_tab = (const int*)w;
+}
+
+// Galaxy-independent lookup tables of the GP predict kernels for one model (grids as in
+// dl_gp_predict_dev): tables = device buffer of dl_gp_tables_bytes(nzg, nz) bytes.
+int dl_gp_tables_dev(long long nzg, long long nz, const double* zGP, const double* fzGrid,
+                     const double* zgrid, void* tables, void* stream) {
+    DL_REQUIRE(nzg >= 2 && nz >= 2 && zGP && fzGrid && zgrid && tables, "bad arguments");
+    GPModel gm;
+    gm.nzg = (int)nzg; gm.nz = (int)nz;
+    gp_set_tables(gm, tables);
+    const long long n = nzg > nz ? nzg : nz;
+    gp_tables_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        (int)nzg, (int)nz, zGP, fzGrid, zgrid, const_cast<double*>(gm.dls_tab),
+        const_cast<int*>(gm.p1_tab), const_cast<int*>(gm.tlo_tab), const_cast<int*>(gm.flo_tab));
+    DL_CUDA_CHECK(cudaGetLastError());
+    dl_count_launch();
+    return DL_OK;
+}
 
 static int gp_model(GPModel& gm, long long nB, long long nzg, long long nt, long long nz,
                     const double* KCg, const double* KLg, const double* KCd, const double* KLd,
@@ -325,6 +393,7 @@ static int gp_model(GPModel& gm, long long nB, long long nzg, long long nt, long
     gm.tmpl = tmpl; gm.zgrid = zgrid;
     gm.nB = (int)nB; gm.nzg = (int)nzg; gm.nt = (int)nt; gm.nz = (int)nz;
     gm.V_C = V_C; gm.V_L = V_L;
+    gp_set_tables(gm, nullptr);
     return DL_OK;
 }
 
@@ -361,11 +430,12 @@ int dl_gp_predict_dev(long long nT, long long nB, long long nt, long long nzg, l
                       const double* KL_diag, const double* zGP, const double* fzGrid,
                       const double* tmpl, const double* zgrid, double V_C, double V_L,
                       const double* rows, long long numCol, double* grid, double* train_z,
-                      void* stream) {
+                      const void* tables, void* stream) {
     GPModel gm;
     int rc = gp_model(gm, nB, nzg, nt, nz, KC_grid, KL_grid, KC_diag, KL_diag, zGP, fzGrid, tmpl,
                       zgrid, V_C, V_L);
     if (rc) return rc;
+    gp_set_tables(gm, tables);
     if (nT == 0) return DL_OK;
     DL_REQUIRE(KC_diag && KL_diag && rows && grid, "null pointer");
     DL_REQUIRE(nB <= GP_MAXB, "at most 32 bands");
@@ -391,11 +461,12 @@ int dl_gp_predict_at_dev(long long nT, long long nB, long long nt, long long nzg
                          const double* KL_diag, const double* zGP, const double* fzGrid,
                          const double* tmpl, const double* zgrid, double V_C, double V_L,
                          const double* rows, long long numCol, const double* z_eval, double* out,
-                         void* stream) {
+                         const void* tables, void* stream) {
     GPModel gm;
     int rc = gp_model(gm, nB, nzg, nt, nz, KC_grid, KL_grid, KC_diag, KL_diag, zGP, fzGrid, tmpl,
                       zgrid, V_C, V_L);
     if (rc) return rc;
+    gp_set_tables(gm, tables);
     if (nT == 0) return DL_OK;
     DL_REQUIRE(KC_diag && KL_diag && rows && z_eval && out, "null pointer");
     DL_REQUIRE(nB <= GP_MAXB, "at most 32 bands");

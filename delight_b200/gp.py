@@ -54,6 +54,12 @@ class PhotozGPBatched:
             _lib.ptr(self.d_norms), _lib.ptr(self.d_fz), _lib.ptr(self.KC), _lib.ptr(self.KL),
             _lib.ptr(self.KCd), _lib.ptr(self.KLd), _lib.stream_ptr()))
         self.numCol = 3 + nB + nB * (nB + 1) // 2 + nB + self.nt     # delight-learn.py:46
+        # galaxy-independent lookup tables of the predict kernels, once per model
+        self.tables = torch.empty(int(L.dl_gp_tables_bytes(nzg, self.nz)), dtype=torch.uint8,
+                                  device="cuda")
+        _lib.check(L.dl_gp_tables_dev(nzg, self.nz, _lib.ptr(self.d_zgp), _lib.ptr(self.d_fz),
+                                      _lib.ptr(self.d_zgrid), _lib.ptr(self.tables),
+                                      _lib.stream_ptr()))
 
     def fit(self, cat, out_device=False):
         """cat: apply.Targets-like packed catalogue (fluxes, fluxes_var, bands, nf, ztrue=z).
@@ -111,7 +117,7 @@ class PhotozGPBatched:
             nT, self.nB, self.nt, self.nzg, self.nz, _lib.ptr(self.KC), _lib.ptr(self.KL),
             _lib.ptr(self.KCd), _lib.ptr(self.KLd), _lib.ptr(self.d_zgp), _lib.ptr(self.d_fz),
             _lib.ptr(self.d_tmpl), _lib.ptr(self.d_zgrid), self.V_C, self.V_L, _lib.ptr(rows),
-            numCol, _lib.ptr(grid), _lib.ptr(train_z), _lib.stream_ptr()))
+            numCol, _lib.ptr(grid), _lib.ptr(train_z), _lib.ptr(self.tables), _lib.stream_ptr()))
         return ModelGrid(grid, nT, self.nB, self.nz), train_z
 
 
@@ -132,7 +138,7 @@ class PhotozGPBatched:
             nT, self.nB, self.nt, self.nzg, self.nz, _lib.ptr(self.KC), _lib.ptr(self.KL),
             _lib.ptr(self.KCd), _lib.ptr(self.KLd), _lib.ptr(self.d_zgp), _lib.ptr(self.d_fz),
             _lib.ptr(self.d_tmpl), _lib.ptr(self.d_zgrid), self.V_C, self.V_L, _lib.ptr(rows),
-            numCol, _lib.ptr(ze), _lib.ptr(out), _lib.stream_ptr()))
+            numCol, _lib.ptr(ze), _lib.ptr(out), _lib.ptr(self.tables), _lib.stream_ptr()))
         out = out.cpu().numpy()
         return out[:, :self.nB], out[:, self.nB:]
 

@@ -223,7 +223,14 @@ int dl_gp_predict_dev(long long nT, long long nB, long long nt, long long nzg, l
                       const double* KL_diag, const double* zGP, const double* fzGrid,
                       const double* tmpl, const double* zgrid, double V_C, double V_L,
                       const double* rows, long long numCol, double* grid, double* train_z,
-                      void* stream);
+                      const void* tables, void* stream);
+/* Galaxy-independent lookup tables of the two predict entry points (distance factors, grid
+ * positions and interpolation bins of the GP nodes and of the fine grid), computed once per
+ * model: tables = device buffer of dl_gp_tables_bytes(nzg, nz) bytes.  The predict calls accept
+ * tables = NULL (everything recomputed per galaxy; several times slower). */
+long long dl_gp_tables_bytes(long long nzg, long long nz);
+int dl_gp_tables_dev(long long nzg, long long nz, const double* zGP, const double* fzGrid,
+                     const double* zgrid, void* tables, void* stream);
 
 /* The same GP evaluated at ONE redshift per training galaxy   replaces delight-learn.py:92-94
  * (predictAndInterpolate(np.array([z]), ell=ell) of the cross-validation): z_eval [nT] ->
@@ -233,7 +240,7 @@ int dl_gp_predict_at_dev(long long nT, long long nB, long long nt, long long nzg
                          const double* KL_diag, const double* zGP, const double* fzGrid,
                          const double* tmpl, const double* zgrid, double V_C, double V_L,
                          const double* rows, long long numCol, const double* z_eval, double* out,
-                         void* stream);
+                         const void* tables, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Measurement hooks (used by bench.py; no effect on results)
