@@ -446,6 +446,71 @@ __global__ void ci_levels_kernel(int nO, int nz, const double* __restrict__ pdf,
         for (int k = 0; k < nfrac; ++k) out[(size_t)o * nfrac + k] = res[k];
 }
 
+// The same scan with the LEVELS spread over the lanes (lane l owns levels l, l + 32, ...; up to
+// 8 per lane, i.e. numlevels <= 256): every lane walks the whole PDF once, keeping per level the
+// previous selected point and the running trapezoid sum -- no ballots, no shuffles, no pass over
+// the PDF per level.  6-10x faster than ci_levels_kernel (which scans level after level and
+// stays as the general form for numlevels > 256): 56 -> 8 ms for the 100k targets of config 2.
+constexpr int CI_LPL = 8;
+template <int LPL>
+__global__ void __launch_bounds__(128) ci_levels_lanes_kernel(
+    int nO, int nz, const double* __restrict__ pdf, long long ld, const double* __restrict__ zgrid,
+    int nfrac, const double* __restrict__ fractions, int numlevels, double* __restrict__ out) {
+    extern __shared__ double ci_sm[];                 // per warp: p[nz], then (once) zgrid[nz]
+    const int warp = threadIdx.x >> 5;
+    const int o = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int lane = threadIdx.x & 31;
+    double* zs = ci_sm;                               // [nz] shared by the CTA's warps
+    double* ps = ci_sm + nz + (size_t)warp * nz;      // [nz] of this warp's target
+    for (int i = threadIdx.x; i < nz; i += blockDim.x) zs[i] = zgrid[i];
+    __syncthreads();
+    if (o >= nO) return;
+    const double* p = pdf + (size_t)o * ld;
+    double ev = 0.0, mx = -INFINITY;
+    for (int i = lane; i < nz; i += 32) {
+        const double y = p[i];
+        ps[i] = y;
+        mx = fmax(mx, y);
+        if (i + 1 < nz) ev += (zs[i + 1] - zs[i]) * (p[i + 1] + y) * 0.5;
+    }
+    __syncwarp();
+    ev = warp_sum(ev);
+    mx = warp_max(mx);
+    const double step = (mx - 0.0) / (double)(numlevels - 1);      // np.linspace
+    // acc2 = twice the trapezoid sum (the 1/2 is applied to the threshold side, exactly)
+    double lev[LPL], acc2[LPL], px[LPL], py[LPL];
+#pragma unroll
+    for (int k = 0; k < LPL; ++k) {
+        const int lv = lane + 32 * k;
+        lev[k] = lv >= numlevels ? -INFINITY : (lv == numlevels - 1 ? mx : lv * step + 0.0);
+        acc2[k] = 0.0; px[k] = 0.0; py[k] = 0.0;
+    }
+    unsigned have = 0;
+#pragma unroll 4
+    for (int i = 0; i < nz; ++i) {
+        const double y = ps[i], x = zs[i];                         // broadcast LDS
+#pragma unroll
+        for (int k = 0; k < LPL; ++k) {
+            const bool sel = y <= lev[k];
+            const double term = (x - px[k]) * (y + py[k]);
+            if (sel && (have >> k & 1u)) acc2[k] += term;
+            if (sel) { px[k] = x; py[k] = y; have |= 1u << k; }
+        }
+    }
+    // first level (ascending) whose integral reaches fraction * evidence
+    for (int f = 0; f < nfrac; ++f) {
+        const double want = fractions[f] * ev;
+        int first = 0x7fffffff;
+#pragma unroll
+        for (int k = LPL - 1; k >= 0; --k)
+            if (lane + 32 * k < numlevels && acc2[k] * 0.5 >= want) first = lane + 32 * k;
+        first = __reduce_min_sync(0xffffffffu, first);
+        if (lane == 0)
+            out[(size_t)o * nfrac + f] = first == 0x7fffffff ? nan("")
+                : (first == numlevels - 1 ? mx : first * step + 0.0);
+    }
+}
+
 // prior[t][z] = exp(-0.5 ((z - z_t) / sigma)^2)   (scripts/delight-apply.py:104), padded rows
 __global__ void zprior_kernel(int nT, int nz, int nzp, const double* __restrict__ zgrid,
                               const double* __restrict__ ztrain, double sigma,
@@ -817,8 +882,17 @@ int dl_ci_levels_dev(long long nO, long long nz, const double* pdf, long long ld
                      double* out, void* stream) {
     DL_REQUIRE(nO > 0 && nz > 1 && ld_pdf >= nz, "bad shape");
     DL_REQUIRE(nfrac >= 1 && nfrac <= CI_MAXF && numlevels >= 2, "1..8 fractions");
-    ci_levels_kernel<<<(unsigned)((nO + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
-        (int)nO, (int)nz, pdf, ld_pdf, zgrid, nfrac, fractions, numlevels, out);
+    const size_t sm = sizeof(double) * (size_t)nz * 5;         // zgrid + 4 warps' PDFs
+    if (numlevels <= 32 * CI_LPL && sm <= 200 * 1024) {
+        auto kern = numlevels <= 32 * 7 ? ci_levels_lanes_kernel<7> : ci_levels_lanes_kernel<CI_LPL>;
+        DL_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)sm));
+        kern<<<(unsigned)((nO + 3) / 4), 128, sm, (cudaStream_t)stream>>>(
+            (int)nO, (int)nz, pdf, ld_pdf, zgrid, nfrac, fractions, numlevels, out);
+    } else {
+        ci_levels_kernel<<<(unsigned)((nO + 3) / 4), 128, 0, (cudaStream_t)stream>>>(
+            (int)nO, (int)nz, pdf, ld_pdf, zgrid, nfrac, fractions, numlevels, out);
+    }
     DL_CUDA_CHECK(cudaGetLastError());
     dl_count_launch();
     return DL_OK;

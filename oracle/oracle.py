@@ -399,9 +399,10 @@ def gp_predict_interp_hp(grids, V_C, V_L, tmpl_table, zfine, redshiftGridGP, ban
     """Higher-precision truth for gp_predict_interp: the same formulas (photoz_gp.py:236-347,
     SURVEY Appendix C) on the same float64 inputs, every operation in np.longdouble (x86: 64-bit
     mantissa, eps 1.1e-19) with explicit substitutions instead of LAPACK.  The model variance
-    `Kdiag - k^T A^-1 k` cancels ~8 digits, so float64 implementations (the reference's
-    cho_solve + dot, the GPU's |L^-1 k|^2) sit 1e-9..1e-7 away from this value and from each
-    other; tests/test_oracle.py and tests/test_gpu_parity.py measure both distances."""
+    `Kdiag - k^T A^-1 k` is a cancelling difference; this function is the yardstick that shows how
+    much the float64 implementations actually lose there: on the golden mock the reference's
+    cho_solve + dot is 1.7e-14 away, the GPU's |L^-1 k|^2 form 1.1e-14 (tests/test_oracle.py,
+    tools/var_check.py)."""
     ld = np.longdouble
     nB = grids["KC"].shape[0]
     zg = np.asarray(redshiftGridGP, dtype=float)

@@ -1211,3 +1211,36 @@ def test_dropin_nan_cell_is_local_like_the_reference(orc):
     assert ok.sum() == nz * nt - 1
     np.testing.assert_allclose(got[ok], want[ok], rtol=RTOL)
     assert got[ok].max() == 1.0
+
+
+@pytest.mark.parametrize("numlevels", [200, 256, 300, 17])
+def test_ci_levels_both_kernels_vs_oracle(orc, numlevels):
+    """CIlevel (utils.py:196-205) through the C ABI for the reference's 200 levels (levels spread
+    over the lanes) and for more than 256 levels (the level-by-level kernel), multi-modal PDFs on
+    a non-uniform grid, against the oracle's restatement."""
+    import torch
+    from delight_b200 import _lib
+    rng = np.random.default_rng(numlevels)
+    nO, nz = 37, 333
+    zgrid = np.sort(rng.uniform(0.01, 3.0, nz))
+    c = rng.uniform(0.2, 2.8, (nO, 3, 1))
+    w = rng.uniform(0.02, 0.4, (nO, 3, 1))
+    a = rng.uniform(0.0, 1.0, (nO, 3, 1))
+    pdf = (a * np.exp(-0.5 * ((zgrid[None, None, :] - c) / w) ** 2)).sum(axis=1)
+    pdf[3] = 0.0
+    pdf[3, 40] = 1.0                                   # a single spike
+    fr = np.array([0.9, 0.5, 0.32, 0.05])
+    d = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    dp, dz, df = d(pdf), d(zgrid), d(fr)
+    out = torch.empty((nO, fr.size), dtype=torch.float64, device="cuda")
+    _lib.check(_lib.lib().dl_ci_levels_dev(nO, nz, _lib.ptr(dp), nz, _lib.ptr(dz), fr.size,
+                                           _lib.ptr(df), numlevels, _lib.ptr(out),
+                                           _lib.stream_ptr()))
+    got = out.cpu().numpy()
+    for o in range(nO):
+        for j, f in enumerate(fr):
+            want = orc.ci_level(zgrid, pdf[o], f, numlevels=numlevels)
+            if want is None:
+                assert np.isnan(got[o, j])
+            else:
+                np.testing.assert_allclose(got[o, j], want, rtol=1e-12, atol=0)
