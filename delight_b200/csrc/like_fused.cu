@@ -805,10 +805,13 @@ int dl_like_fused_dev(long long nO, long long nT, long long nz, long long nB, in
     };
 
     // 1. anchor exponent per target: max of -chi2/2 over a strided sample of training galaxies
-    const long long nS_want = env_int("DL_FUSED_NSAMPLE", 64);
-    const long long nS = nT < nS_want ? nT : nS_want;
+    //    (every stride-th galaxy, spread over the whole catalogue: it may be sorted)
+    long long nS_want = env_int("DL_FUSED_NSAMPLE", 64);
+    if (nS_want < 1) nS_want = 1;
+    const long long stride = (nT + nS_want - 1) / nS_want;
+    const long long nS = (nT + stride - 1) / stride;
     p.rescue = 0;
-    set_blocks(nS, (int)(nT / nS), pl.TT < 16 ? pl.TT : 16);
+    set_blocks(nS, (int)stride, pl.TT < 16 ? pl.TT : 16);
     int rc = launch_fused(nf, zdep, het, MODE_SAMPLE, p, stream, false);
     if (rc != DL_OK) return rc;
     anchor_fold_kernel<<<(unsigned)nO, 128, 0, stream>>>((int)nO, nf, TCS, tconst, Akey, flag,

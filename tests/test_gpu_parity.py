@@ -205,23 +205,24 @@ def test_fast_math_accuracy():
 # ------------------------------------------------------------------------------------------------
 # fused apply path
 # ------------------------------------------------------------------------------------------------
-def _check_fused(res, ref, K, atol_scale=1e-290):
+def _check_fused(res, ref, K, atol_scale=1e-290, rtol=None):
     pdf_ref = ref["pdf"]
-    assert_close(res["pdf"], pdf_ref, pdf_ref.max(axis=1, keepdims=True) * atol_scale)
+    assert_close(res["pdf"], pdf_ref, pdf_ref.max(axis=1, keepdims=True) * atol_scale, rtol)
     if ref.get("evid") is not None and res.get("evid") is not None:
-        assert_close(res["evid"], ref["evid"], ref["evid"].max(axis=1, keepdims=True) * atol_scale)
+        assert_close(res["evid"], ref["evid"], ref["evid"].max(axis=1, keepdims=True) * atol_scale,
+                     rtol)
     if K:
         # indices must agree exactly wherever the evidence is not in the reference's own
         # denormal / underflow range (there the order is decided by which side flushed to zero)
         sig = ref["top_ev"] > ref["top_ev"].max(axis=1, keepdims=True) * 1e-250
         np.testing.assert_array_equal(res["top_idx"][sig], ref["top_idx"][sig])
         assert_close(res["top_ev"], ref["top_ev"],
-                     ref["top_ev"].max(axis=1, keepdims=True) * atol_scale)
+                     ref["top_ev"].max(axis=1, keepdims=True) * atol_scale, rtol)
 
 
-def assert_close(a, b, atol):
+def assert_close(a, b, atol, rtol=None):
     err = np.abs(a - b)
-    ok = err <= RTOL * np.abs(b) + atol
+    ok = err <= (rtol or RTOL) * np.abs(b) + atol
     assert ok.all(), "max rel err %.3e at %s" % (
         (err / np.maximum(np.abs(b), 1e-300))[~ok].max(), np.argwhere(~ok)[:5].tolist())
 
@@ -1244,3 +1245,54 @@ def test_ci_levels_both_kernels_vs_oracle(orc, numlevels):
                 assert np.isnan(got[o, j])
             else:
                 np.testing.assert_allclose(got[o, j], want, rtol=1e-12, atol=0)
+
+
+def test_fused_rescue_pass_redoes_targets_far_above_their_anchor(orc, monkeypatch):
+    """The anchor exponent of a target comes from a SAMPLE of training galaxies; when the best
+    cell lies more than e^500 above it the target is flagged and redone with the exact maximum.
+    Force that: one sampled training galaxy only (DL_FUSED_NSAMPLE=1), signal-to-noise 1000 (chi2
+    differences ~1e6).  Without the rescue the same call must come out wrong (which proves that
+    the rescue ran and was needed); with it every target matches the oracle."""
+    from delight_b200 import apply
+    rng = np.random.default_rng(77)
+    nO, nT, nz, nB = 70, 150, 200, 5
+    zgrid = np.linspace(0.01, 3.0, nz)
+    mm = 1e5 * rng.uniform(0.5, 2.0, (1, nT, nB)) * (1 + 0.5 * np.sin(
+        zgrid[:, None, None] * rng.uniform(1, 4, (1, nT, nB))))
+    mc = (mm * 1e-3) ** 2
+    zt = rng.uniform(0.01, 3.0, nT)
+    src = rng.integers(1, nT, nO)                       # never the sampled galaxy 0
+    fl = mm[rng.integers(0, nz, nO), src] * 4e-10
+    fv = (1e-3 * fl) ** 2
+    K = 10
+    ref = orc.apply_fused(fl, fv, np.full(nO, nB), np.tile(np.arange(nB), (nO, 1)), mm, mc,
+                          orc.z_prior(zgrid, zt, 0.5), zgrid, np.ones(nz), np.full(nz, 0.25), K,
+                          want_evid=True)
+    grid = apply.ModelGrid.from_legacy(mm, mc)
+    prior = grid.gaussian_prior(zgrid, zt, 0.5)
+    t = apply.Targets.full(fl, fv)
+    monkeypatch.setenv("DL_FUSED_NSAMPLE", "1")
+    monkeypatch.setenv("DL_FUSED_NORESCUE", "1")
+    bad = apply.apply_fused(grid, prior, zgrid, t, ell_hat=1.0, ell_var=0.25, K=K, want_evid=True)
+    scale = ref["pdf"].max(axis=1, keepdims=True)
+    wrong = ~np.all(np.abs(bad["pdf"] - ref["pdf"]) <= 1e-6 * np.abs(ref["pdf"]) + 1e-200 * scale,
+                    axis=1)
+    assert wrong.sum() > nO // 2, "the scenario does not exceed the anchor by e^500"
+    monkeypatch.delenv("DL_FUSED_NORESCUE")
+    res = apply.apply_fused(grid, prior, zgrid, t, ell_hat=1.0, ell_var=0.25, K=K, want_evid=True)
+    # chi2 is a difference of O(nf * snr^2) terms: the absolute rounding error of the exponent
+    # grows with snr^2 in the reference too (same bound as test_fused_extreme_dynamic_range);
+    # measured here: 1.7e-9
+    rtol = 1e-13 * nB * 1000.0 ** 2
+    _check_fused(res, ref, K, rtol=rtol)
+    # a mixed batch: flagged and unflagged targets in the same tiles
+    fv2 = fv.copy()
+    fv2[::2] = (0.05 * fl[::2]) ** 2                    # every other target at S/N 20
+    ref2 = orc.apply_fused(fl, fv2, np.full(nO, nB), np.tile(np.arange(nB), (nO, 1)), mm, mc,
+                           orc.z_prior(zgrid, zt, 0.5), zgrid, np.ones(nz), np.full(nz, 0.25), K,
+                           want_evid=True)
+    res2 = apply.apply_fused(grid, prior, zgrid, apply.Targets.full(fl, fv2), ell_hat=1.0,
+                             ell_var=0.25, K=K, want_evid=True)
+    _check_fused(res2, ref2, K, rtol=rtol)
+    np.testing.assert_allclose(res2["pdf"][::2], ref2["pdf"][::2], rtol=RTOL,
+                               atol=1e-290 * ref2["pdf"].max())     # the S/N 20 half: 1e-9
