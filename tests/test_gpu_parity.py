@@ -1247,7 +1247,8 @@ def test_ci_levels_both_kernels_vs_oracle(orc, numlevels):
                 np.testing.assert_allclose(got[o, j], want, rtol=1e-12, atol=0)
 
 
-def test_fused_rescue_pass_redoes_targets_far_above_their_anchor(orc, monkeypatch):
+@pytest.mark.parametrize("zdep,het", [(False, False), (True, False), (False, True)])
+def test_fused_rescue_pass_redoes_targets_far_above_their_anchor(orc, monkeypatch, zdep, het):
     """The anchor exponent of a target comes from a SAMPLE of training galaxies; when the best
     cell lies more than e^500 above it the target is flagged and redone with the exact maximum.
     Force that: one sampled training galaxy only (DL_FUSED_NSAMPLE=1), signal-to-noise 1000 (chi2
@@ -1265,21 +1266,32 @@ def test_fused_rescue_pass_redoes_targets_far_above_their_anchor(orc, monkeypatc
     fl = mm[rng.integers(0, nz, nO), src] * 4e-10
     fv = (1e-3 * fl) ** 2
     K = 10
-    ref = orc.apply_fused(fl, fv, np.full(nO, nB), np.tile(np.arange(nB), (nO, 1)), mm, mc,
-                          orc.z_prior(zgrid, zt, 0.5), zgrid, np.ones(nz), np.full(nz, 0.25), K,
-                          want_evid=True)
+    eh = rng.uniform(0.5, 2, nz) if zdep else np.ones(nz)
+    ev = rng.uniform(0.1, 0.5, nz) if zdep else np.full(nz, 0.25)
+    bands = np.tile(np.arange(nB), (nO, 1))
+    nfs = np.full(nO, nB)
+    if het:                                             # 4 of the 5 bands, a different one dropped
+        nfs[:] = nB - 1
+        for o in range(nO):
+            keep = np.delete(np.arange(nB), o % nB)
+            bands[o, :nB - 1] = keep
+            fl[o, :nB - 1] = fl[o, keep]
+            fv[o, :nB - 1] = fv[o, keep]
+    ref = orc.apply_fused(fl, fv, nfs, bands, mm, mc, orc.z_prior(zgrid, zt, 0.5), zgrid, eh, ev,
+                          K, want_evid=True)
     grid = apply.ModelGrid.from_legacy(mm, mc)
     prior = grid.gaussian_prior(zgrid, zt, 0.5)
-    t = apply.Targets.full(fl, fv)
+    t = apply.Targets(fl, fv, bands, nfs)
+    ell = dict(ell_hat=eh if zdep else 1.0, ell_var=ev if zdep else 0.25)
     monkeypatch.setenv("DL_FUSED_NSAMPLE", "1")
     monkeypatch.setenv("DL_FUSED_NORESCUE", "1")
-    bad = apply.apply_fused(grid, prior, zgrid, t, ell_hat=1.0, ell_var=0.25, K=K, want_evid=True)
+    bad = apply.apply_fused(grid, prior, zgrid, t, K=K, want_evid=True, **ell)
     scale = ref["pdf"].max(axis=1, keepdims=True)
     wrong = ~np.all(np.abs(bad["pdf"] - ref["pdf"]) <= 1e-6 * np.abs(ref["pdf"]) + 1e-200 * scale,
                     axis=1)
     assert wrong.sum() > nO // 2, "the scenario does not exceed the anchor by e^500"
     monkeypatch.delenv("DL_FUSED_NORESCUE")
-    res = apply.apply_fused(grid, prior, zgrid, t, ell_hat=1.0, ell_var=0.25, K=K, want_evid=True)
+    res = apply.apply_fused(grid, prior, zgrid, t, K=K, want_evid=True, **ell)
     # chi2 is a difference of O(nf * snr^2) terms: the absolute rounding error of the exponent
     # grows with snr^2 in the reference too (same bound as test_fused_extreme_dynamic_range);
     # measured here: 1.7e-9
@@ -1288,11 +1300,10 @@ def test_fused_rescue_pass_redoes_targets_far_above_their_anchor(orc, monkeypatc
     # a mixed batch: flagged and unflagged targets in the same tiles
     fv2 = fv.copy()
     fv2[::2] = (0.05 * fl[::2]) ** 2                    # every other target at S/N 20
-    ref2 = orc.apply_fused(fl, fv2, np.full(nO, nB), np.tile(np.arange(nB), (nO, 1)), mm, mc,
-                           orc.z_prior(zgrid, zt, 0.5), zgrid, np.ones(nz), np.full(nz, 0.25), K,
-                           want_evid=True)
-    res2 = apply.apply_fused(grid, prior, zgrid, apply.Targets.full(fl, fv2), ell_hat=1.0,
-                             ell_var=0.25, K=K, want_evid=True)
+    ref2 = orc.apply_fused(fl, fv2, nfs, bands, mm, mc, orc.z_prior(zgrid, zt, 0.5), zgrid, eh,
+                           ev, K, want_evid=True)
+    res2 = apply.apply_fused(grid, prior, zgrid, apply.Targets(fl, fv2, bands, nfs), K=K,
+                             want_evid=True, **ell)
     _check_fused(res2, ref2, K, rtol=rtol)
     np.testing.assert_allclose(res2["pdf"][::2], ref2["pdf"][::2], rtol=RTOL,
                                atol=1e-290 * ref2["pdf"].max())     # the S/N 20 half: 1e-9
