@@ -77,6 +77,14 @@ constexpr int ZJ = 2;         // redshifts a lane processes jointly (independent
 #define DL_CFG1_NF 9          // homogeneous band sets from here on use config 1
 #endif
 
+#ifndef DL_GRP_ROLL_NF
+#define DL_GRP_ROLL_NF 6       // from here on the two z-groups of a stage are a rolled loop
+#endif
+constexpr int GRP_ROLL_NF = DL_GRP_ROLL_NF;
+#ifndef DL_TGT_UNROLL
+#define DL_TGT_UNROLL 4        // target (pair) loop unrolled in the register-model kernels
+#endif
+constexpr int TGT_UNROLL = DL_TGT_UNROLL;
 constexpr int BAND_UNROLL0 = DL_BAND_UNROLL0;   // (macros are not expanded inside #pragma unroll)
 constexpr int BAND_UNROLL1 = DL_BAND_UNROLL1;
 
@@ -482,11 +490,13 @@ fused_like_kernel(const FusedParams p) {
         mbar_wait(&full[cs], cph);
         const double* st = stage + (size_t)cs * ROWS * FZC;
         const int z0 = chunk * FZC;
-        // fully unrolled for the register-cached variants; rolled when the model values stay in
-        // the stage (code size and compile time: 4 x NF bands x groups otherwise) and in SAMPLE
+        // z-group loop: unrolled for the small register-cached variants; rolled from 6 bands on
+        // (a fully unrolled step is 53 KB of SASS at 6 bands, beyond the 32 KB instruction cache:
+        // 6 % no-instruction stalls, 1.0998 -> 1.0891 s), when the model values stay in the
+        // stage (code size and compile time: 4 x NF bands x groups otherwise) and in SAMPLE
         // mode (no branch separates the targets there: unrolled, the scheduler interleaves all
         // eight target visits of a step and spills 1.7 KB per thread)
-#pragma unroll (SMODEL ? 1 : FZT / ZJ)
+#pragma unroll (SMODEL || NF >= GRP_ROLL_NF ? 1 : FZT / ZJ)
         for (int grp = 0; grp < FZT / ZJ; ++grp) {
             const int zl = grp * 32 * ZJ + lane;      // cells: zl + 32 c, c < ZJ
             constexpr int RN = SMODEL ? 1 : NF;
@@ -514,7 +524,7 @@ fused_like_kernel(const FusedParams p) {
                     zot[c] = zd[0]; ztt[c] = zd[FZC]; zoo[c] = zd[2 * FZC]; zev[c] = zd[3 * FZC];
                 }
             }
-#pragma unroll (SMODEL || SAMPLE ? 1 : FTO)
+#pragma unroll (SMODEL || SAMPLE ? 1 : TGT_UNROLL)
             for (int o = 0; o < FTO; o += TP) {
                 // E[] is rotated once per target group so the loop can stay rolled with the
                 // accumulators in registers (FTO / TP rotations restore the order)
