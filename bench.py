@@ -332,13 +332,12 @@ def config2_templatefit(data, budget_s=6.0):
     h_met = torch.empty((nO, 8 + len(CL)), dtype=torch.float64).pin_memory()
 
     def e2e():
+        # host catalogue in, PDFs + metrics into pinned host arrays; the copies of one chunk of
+        # targets overlap the kernels of the next (apply.apply_fused_to_host)
         t = apply.Targets.full(h_fl.numpy(), h_fv.numpy(), ztrue)
-        t._dev = {("nf", nB): (h_fl.cuda(non_blocking=True), h_fv.cuda(non_blocking=True), None,
-                               None)}
-        r = run(t)
-        h_pdf.copy_(r["pdf"], non_blocking=True)
-        h_met.copy_(r["metrics"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        apply.apply_fused_to_host(grid, prior, zgrid, t, {"pdf": h_pdf, "metrics": h_met},
+                                  ell_hat=1.0, ell_var=1e24, K=0, want_metrics=True,
+                                  confidence_levels=CL, workspace=ws)
     e2e()
     t0 = time.perf_counter()
     e2e()

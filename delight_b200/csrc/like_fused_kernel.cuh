@@ -56,7 +56,7 @@ constexpr int ZJ = 2;         // redshifts a lane processes jointly (independent
 #define DL_ROTPROD 1
 #endif
 #ifndef DL_CHI2_EARLY
-#define DL_CHI2_EARLY 0
+#define DL_CHI2_EARLY 1
 #endif
 #ifndef DL_BAND_UNROLL0
 #define DL_BAND_UNROLL0 4     // pass-0 band loop beyond REGNF bands

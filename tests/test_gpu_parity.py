@@ -1307,3 +1307,31 @@ def test_fused_rescue_pass_redoes_targets_far_above_their_anchor(orc, monkeypatc
     _check_fused(res2, ref2, K, rtol=rtol)
     np.testing.assert_allclose(res2["pdf"][::2], ref2["pdf"][::2], rtol=RTOL,
                                atol=1e-290 * ref2["pdf"].max())     # the S/N 20 half: 1e-9
+
+
+def test_apply_fused_to_host_matches_apply_fused(golden, sdss):
+    """Chunked apply with the device-to-host copies overlapped on a second stream: same rows, in
+    target order, as the one-shot call (config-2 twin of the golden fixture, uneven chunks)."""
+    import torch
+    from delight_b200 import apply
+    g = golden("templatefit")
+    f_mod = g["f_mod"]
+    nz = f_mod.shape[0]
+    grid = apply.ModelGrid.from_legacy(f_mod, np.zeros_like(f_mod))
+    prior = grid.template_prior(sdss["zgrid"], g["p_t"], g["p_z_t"])
+    reps = 9
+    t = apply.Targets(np.tile(sdss["ta_flux"], (reps, 1)), np.tile(sdss["ta_var"], (reps, 1)),
+                      np.tile(sdss["ta_bands"], (reps, 1)), np.tile(sdss["ta_nb"], reps),
+                      np.tile(sdss["ta_z"], reps))
+    CL = [0.1, 0.5, 0.68, 0.95]
+    kw = dict(ell_hat=1.0, ell_var=1e24, K=0, want_metrics=True, confidence_levels=CL)
+    one = apply.apply_fused(grid, prior, sdss["zgrid"], t, **kw)
+    nO = len(t)
+    host = {"pdf": torch.empty((nO, nz), dtype=torch.float64).pin_memory(),
+            "metrics": torch.empty((nO, 8 + len(CL)), dtype=torch.float64).pin_memory()}
+    apply.apply_fused_to_host(grid, prior, sdss["zgrid"], t, host, chunk=50, **kw)
+    np.testing.assert_allclose(host["pdf"].numpy(), one["pdf"], rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(host["metrics"].numpy(), one["metrics"], rtol=1e-12)
+    n = g["pdfs"].shape[0]
+    np.testing.assert_allclose(host["pdf"].numpy()[:n], g["pdfs"], rtol=RTOL,
+                               atol=1e-290 * g["pdfs"].max())
