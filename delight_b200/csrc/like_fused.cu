@@ -724,7 +724,6 @@ int dl_like_fused_dev(long long nO, long long nT, long long nz, long long nB, in
     DL_REQUIRE(ld_pdf >= nz, "ld_pdf < nz");
     DL_REQUIRE(cov_scale >= 0.0, "cov_scale < 0");
     const bool zdep = ell_hat_z != nullptr && ell_var_z != nullptr;
-    const bool want_E = evid != nullptr || K > 0;
     const long long need = dl_fused_workspace_bytes(nO, nT, nz, evid != nullptr || K == 0);
     DL_REQUIRE(workspace && workspace_bytes >= need, "workspace too small");
     const int nzp = (int)dl_fused_padded_nz(nz);
@@ -864,7 +863,6 @@ int dl_like_fused_dev(long long nO, long long nT, long long nz, long long nB, in
         DL_CUDA_CHECK(cudaGetLastError());
         dl_count_launch();
     }
-    (void)want_E;
     return DL_OK;
 }
 

@@ -8,7 +8,7 @@
 //
 // Work decomposition (B200: 148 SMs, FP64 pipe = 16 lanes / SMSP, 227 KB smem / SM)
 //   unit     = one tile of targets (32 / 64)  x  one block of TT training galaxies  x  ALL z
-//   CTA      = one unit; warps own 4 targets each, warp 0 also drives TMA
+//   CTA      = one unit; warps own 4 targets each; the TMA producer role rotates over the warps
 //              config 0 (<= 8 bands, homogeneous band set): 8 warps, 128-redshift stages, 2 CTAs/SM
 //              config 1 (more bands / per-target band lists): 16 warps, 64-redshift stages, 1 CTA/SM
 //   step     = (z-chunk c, training galaxy k): one pipeline stage of 2 nU + 2 rows (nU band means,
@@ -21,7 +21,7 @@
 //              the model variance folded in (one reciprocal per PAIR of bands), chi2,
 //              (prod var * FTT)^-1/2 by one rsqrt, one table-based exp.  No log, no division.
 //   reduce   = PDF: shared-memory accumulator per (target, z of the chunk), flushed with
-//              red.global.add.f64 at the end of every chunk (the PDF rows of the ~150 tiles in
+//              red.global.add.f64 at the end of every chunk (the PDF rows of the ~110 tiles in
 //              flight stay in L2);  evidence: warp sum per step added to a shared-memory
 //              accumulator per (target, k), complete after the last chunk, stored ONCE.
 //
