@@ -21,6 +21,26 @@ __device__ __forceinline__ double dkey_inv(unsigned long long k) {
 // the variances is carried as mantissa x 2^exponent (renormalised every four bands, so any nf
 // and any unit system stay in range) instead of nf + 2 logs.  That keeps the kernel on the HBM
 // roofline (2 nf 8 B read + 8 B written per cell) instead of the FP64 pipe.
+// 1 / var: MUFU seed + one third-order Newton step (common.cuh) for normal positive finite
+// variances -- what a catalogue produces --, the IEEE intrinsic for anything else (zero,
+// denormal, negative, inf, NaN keep the reference's arithmetic semantics).
+__device__ __forceinline__ double rcp_var(double v) {
+    const unsigned hi = (unsigned)__double2hiint(v);
+    return (hi - 0x00100000u < 0x7fe00000u) ? rcp_fast(v) : __drcp_rn(v);
+}
+
+// prod = m x 2^e with m in [1, 2): strip the exponent of a positive NORMAL double through its
+// bit pattern (4 integer instructions instead of the ilogb / scalbn calls); anything else
+// (zero, denormal, inf, NaN) is left alone and reaches the log as it is.
+__device__ __forceinline__ void strip_exponent(double& prod, int& pexp) {
+    const int hi = __double2hiint(prod);
+    const unsigned ex = ((unsigned)hi >> 20) & 0x7ffu;
+    if (hi > 0 && ex - 1u < 0x7feu) {
+        pexp += (int)ex - 1023;
+        prod = __hiloint2double((hi & 0x800fffff) | 0x3ff00000, __double2loint(prod));
+    }
+}
+
 // VEC: nf even and 16-byte aligned grids -> the nf doubles of a cell are read as double2
 // (half the load instructions and L1 wavefronts of the strided per-thread access).
 template <bool VEC>
@@ -39,29 +59,28 @@ __global__ void __launch_bounds__(256) loglike_kernel(
     double best = -INFINITY;
     for (long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x; cell < ncell;
          cell += (long long)gridDim.x * blockDim.x) {
-        const long long iz = cell / nt;
+        // (64-bit division is ~100 instructions: use the 32-bit one whenever the cell count allows)
+        const long long iz = ncell < 0x7fffffffll ? (long long)((unsigned)cell / (unsigned)nt)
+                                                  : cell / nt;
         const double eh = ell_hat[iz], ev = ell_var[iz];
-        const double iev = 1.0 / ev;
+        const double iev = rcp_var(ev);
         const double* m = f_mod + cell * nf;
         const double* c = f_mod_covar + cell * nf;
-        double ell2 = 0.0, fot = 0.0, ftt = 0.0, foo = 0.0, prod = 1.0;
+        double ell2 = 0.0, fot = 0.0, ftt = 0.0, foo = 0.0, prod = 1.0, rftt = 0.0;
         int pexp = 0;
 #pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
             fot = eh * iev; ftt = iev; foo = eh * eh * iev; prod = 1.0; pexp = 0;
             auto band = [&](int k, double mk, double ck) {
                 const double var = fma(ell2, ck, sh[nf + k]);            // :107
-                const double r = __drcp_rn(var);
+                const double r = rcp_var(var);
                 const double mr = mk * r;
                 fot = fma(mr, sh[k], fot);                               // :108
                 ftt = fma(mr, mk, ftt);                                  // :109
                 foo = fma(sh[2 * nf + k], r, foo);                       // :110
                 if (pass == 1) {                                         // :111-112
                     prod *= var;
-                    if ((k & 3) == 3) {
-                        const int e = ilogb(prod);
-                        if (e > -1000 && e < 1000) { prod = scalbn(prod, -e); pexp += e; }
-                    }
+                    if ((k & 3) == 3) strip_exponent(prod, pexp);
                 }
             };
             if (VEC) {
@@ -75,19 +94,17 @@ __global__ void __launch_bounds__(256) loglike_kernel(
             } else {
                 for (int k = 0; k < nf; ++k) band(k, m[k], c[k]);
             }
-            const double ell = fot / ftt;                                // :113
+            rftt = rcp_var(ftt);
+            const double ell = fot * rftt;                               // :113
             ell2 = ell * ell;
         }
-        const double chi2 = foo - fot * fot / ftt;                       // :115
+        const double chi2 = fma(-(fot * rftt), fot, foo);                // :115
         // logDenom = sum log(2 pi var) + log(2 pi ell_var) + log(FTT / 2 pi)     (:111-117)
         double logden;
         {
-            int e = ilogb(prod);
-            if (e > -1000 && e < 1000) { prod = scalbn(prod, -e); pexp += e; }
-            const double t = ev * ftt;                                   // > 0
-            e = ilogb(t);
-            double tm = t;
-            if (e > -1000 && e < 1000) { tm = scalbn(t, -e); pexp += e; }
+            strip_exponent(prod, pexp);
+            double tm = ev * ftt;                                        // > 0
+            strip_exponent(tm, pexp);
             logden = log(prod * tm) + pexp * LN2 + nf * LOG_2PI;
         }
         const double L = -0.5 * chi2 - 0.5 * logden;                     // :118
