@@ -37,6 +37,10 @@ _SIGS = {
                                     c_ll, c_ll],
     "dl_kernel_parts_interp_dev": [c_ll, c_ll, c_p, c_ll, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
                                    c_ll, c_ll, c_p],
+    "dl_bilininterp_precomputedbins_host": [c_ll, c_ll, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
+                                            c_ll, c_ll],
+    "dl_bilininterp_precomputedbins_dev": [c_ll, c_ll, c_p, c_ll, c_p, c_p, c_p, c_p, c_p, c_p,
+                                           c_p, c_ll, c_ll, c_p],
     "dl_kernel_grids_dev": [c_ll, c_ll, c_ll, c_ll, c_d, c_d, c_p, c_p, c_p, c_p, c_p, c_p, c_p,
                             c_p, c_p, c_p, c_p],
     "dl_fused_chunk": [],

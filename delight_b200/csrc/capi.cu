@@ -200,6 +200,32 @@ int dl_kernel_parts_interp_host(long long NO1, long long NO2, double* Kinterp,
     return DL_OK;
 }
 
+int dl_bilininterp_precomputedbins_host(long long numBands, long long nobj, double* Kinterp,
+                                        const double* v1s, const double* v2s,
+                                        const long long* p1s, const long long* p2s,
+                                        const double* grid1, const double* grid2,
+                                        const double* Kgrid, long long n1, long long n2) {
+    DL_REQUIRE(numBands >= 0 && nobj >= 0 && n1 >= 2 && n2 >= 2, "bad sizes");
+    if (numBands * nobj == 0) return DL_OK;
+    DL_REQUIRE(in_range(p1s, nobj, 0, n1 - 1) && in_range(p2s, nobj, 0, n2 - 1),
+               "bin position out of range");
+    DevBuf dk, dv1, dv2, dp1, dp2, dg1, dg2, dG;
+    TRY(dk.alloc((size_t)numBands * nobj * 8));
+    TRY(dv1.upload(v1s, nobj * 8));
+    TRY(dv2.upload(v2s, nobj * 8));
+    TRY(dp1.upload(p1s, nobj * 8));
+    TRY(dp2.upload(p2s, nobj * 8));
+    TRY(dg1.upload(grid1, n1 * 8));
+    TRY(dg2.upload(grid2, n2 * 8));
+    TRY(dG.upload(Kgrid, (size_t)numBands * n1 * n2 * 8));
+    TRY(dl_bilininterp_precomputedbins_dev(numBands, nobj, dk.as<double>(), nobj, dv1.as<double>(),
+                                           dv2.as<double>(), dp1.as<long long>(),
+                                           dp2.as<long long>(), dg1.as<double>(), dg2.as<double>(),
+                                           dG.as<double>(), n1, n2, nullptr));
+    DL_CUDA_CHECK(cudaMemcpy(Kinterp, dk.p, (size_t)numBands * nobj * 8, cudaMemcpyDeviceToHost));
+    return DL_OK;
+}
+
 }  // extern "C"
 
 // ------------------------------------------------------------------ bookkeeping / measurement

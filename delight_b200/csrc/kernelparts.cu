@@ -204,11 +204,52 @@ __global__ void kernel_parts_interp_kernel(int NO1, int NO2, double* __restrict_
                                               (x - xl) * (y - yl) * G[(p1 + 1) * nzg + p2 + 1]);
 }
 
+// bilininterp_precomputedbins (utils_cy.pyx:25-50): bilinear interpolation of nbands grids
+// Kgrid[b][n1][n2] at the points (v1s[o], v2s[o]) with precomputed bins -> Kinterp[b][o]
+__global__ void bilininterp_kernel(int numBands, int nobj, double* __restrict__ Kinterp,
+                                   long long ld, const double* __restrict__ v1s,
+                                   const double* __restrict__ v2s,
+                                   const long long* __restrict__ p1s,
+                                   const long long* __restrict__ p2s,
+                                   const double* __restrict__ grid1,
+                                   const double* __restrict__ grid2,
+                                   const double* __restrict__ Kgrid, int n1, int n2) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)numBands * nobj) return;
+    const int b = (int)(idx / nobj), o = (int)(idx % nobj);
+    const long long p1 = p1s[o], p2 = p2s[o];
+    const double v1 = v1s[o], v2 = v2s[o];
+    const double dzm2 = 1. / (grid1[p1 + 1] - grid1[p1]) / (grid2[p2 + 1] - grid2[p2]);
+    const double* G = Kgrid + (long long)b * n1 * n2;
+    Kinterp[(long long)b * ld + o] = dzm2 * (
+        (grid1[p1 + 1] - v1) * (grid2[p2 + 1] - v2) * G[p1 * n2 + p2]
+        + (v1 - grid1[p1]) * (grid2[p2 + 1] - v2) * G[(p1 + 1) * n2 + p2]
+        + (grid1[p1 + 1] - v1) * (v2 - grid2[p2]) * G[p1 * n2 + p2 + 1]
+        + (v1 - grid1[p1]) * (v2 - grid2[p2]) * G[(p1 + 1) * n2 + p2 + 1]);
+}
+
 }  // namespace dl
 
 using namespace dl;
 
 extern "C" {
+
+int dl_bilininterp_precomputedbins_dev(long long numBands, long long nobj, double* Kinterp,
+                                       long long ld, const double* v1s, const double* v2s,
+                                       const long long* p1s, const long long* p2s,
+                                       const double* grid1, const double* grid2,
+                                       const double* Kgrid, long long n1, long long n2,
+                                       void* stream) {
+    DL_REQUIRE(numBands >= 0 && nobj >= 0 && n1 >= 2 && n2 >= 2 && ld >= nobj, "bad sizes");
+    if (numBands * nobj == 0) return DL_OK;
+    const long long n = numBands * nobj;
+    bilininterp_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        (int)numBands, (int)nobj, Kinterp, ld, v1s, v2s, p1s, p2s, grid1, grid2, Kgrid, (int)n1,
+        (int)n2);
+    DL_CUDA_CHECK(cudaGetLastError());
+    dl_count_launch();
+    return DL_OK;
+}
 
 static int kp_args(KPArgs& a, long long NO1, long long NO2, long long NC, long long NL,
                    double alpha_C, double alpha_L, const double* amp, const double* mu,

@@ -11,7 +11,8 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["approx_flux_likelihood_cy", "find_positions", "kernel_parts_interp"]
+__all__ = ["approx_flux_likelihood_cy", "find_positions", "kernel_parts_interp",
+           "bilininterp_precomputedbins"]
 
 
 def _view(a, dtype, ndim, name):
@@ -149,3 +150,34 @@ def kernel_parts_interp(NO1, NO2, Kinterp, b1, fz1, p1s, b2, fz2, p2s, fzGrid, K
     """delight/utils_cy.pyx:53-79 (identical twin of photoz_kernels_cy.pyx:9-35)."""
     from .photoz_kernels_cy import kernel_parts_interp as _kpi
     return _kpi(NO1, NO2, Kinterp, b1, fz1, p1s, b2, fz2, p2s, fzGrid, Kgrid)
+
+
+def bilininterp_precomputedbins(numBands, nobj, Kinterp, v1s, v2s, p1s, p2s, grid1, grid2, Kgrid):
+    """delight/utils_cy.pyx:25-50.  Kinterp[b, o] = bilinear interpolation of Kgrid[b] at
+    (v1s[o], v2s[o]) with the bins p1s / p2s found by find_positions."""
+    numBands, nobj = int(numBands), int(nobj)
+    Kinterp = _view(Kinterp, np.float64, 2, "Kinterp")
+    v1s = _view(v1s, np.float64, 1, "v1s")
+    v2s = _view(v2s, np.float64, 1, "v2s")
+    p1s = _view(p1s, np.int64, 1, "p1s")
+    p2s = _view(p2s, np.int64, 1, "p2s")
+    grid1 = _view(grid1, np.float64, 1, "grid1")
+    grid2 = _view(grid2, np.float64, 1, "grid2")
+    Kgrid = _view(Kgrid, np.float64, 3, "Kgrid")
+    if numBands * nobj == 0:
+        return
+    nb, n1, n2 = Kgrid.shape
+    if nb < numBands or grid1.size < n1 or grid2.size < n2 or Kinterp.shape[0] < numBands or \
+            Kinterp.shape[1] < nobj or min(v1s.size, v2s.size, p1s.size, p2s.size) < nobj:
+        raise ValueError("array shapes are inconsistent")
+    for p, n in ((p1s[:nobj], n1), (p2s[:nobj], n2)):
+        if p.size and (p.min() < 0 or p.max() > n - 2):
+            raise ValueError("bin positions outside [0, n-2]")
+    torch = _lib.require_cuda()
+    d_k = torch.empty((numBands, nobj), dtype=torch.float64, device="cuda")
+    args = [_dev(a) for a in (v1s[:nobj], v2s[:nobj], p1s[:nobj], p2s[:nobj], grid1[:n1],
+                              grid2[:n2], Kgrid[:numBands])]
+    _lib.check(_lib.lib().dl_bilininterp_precomputedbins_dev(
+        numBands, nobj, _lib.ptr(d_k), nobj, *[_lib.ptr(a) for a in args], n1, n2,
+        _lib.stream_ptr()))
+    Kinterp[:numBands, :nobj] = d_k.cpu().numpy()

@@ -103,6 +103,21 @@ int dl_kernel_parts_interp_dev(long long NO1, long long NO2, double* Kinterp, lo
                                const double* fzGrid, const double* Kgrid, long long nB,
                                long long nzg, void* stream);
 
+/* (6) bilininterp_precomputedbins        replaces delight/utils_cy.pyx:25-50 (used by the
+ *     reference's tests only, tests/test_utils.py:89-115; here for a complete utils_cy surface)
+ *     Kgrid [numBands][n1][n2], Kinterp [numBands][nobj] overwritten. */
+int dl_bilininterp_precomputedbins_host(long long numBands, long long nobj, double* Kinterp,
+                                        const double* v1s, const double* v2s,
+                                        const long long* p1s, const long long* p2s,
+                                        const double* grid1, const double* grid2,
+                                        const double* Kgrid, long long n1, long long n2);
+int dl_bilininterp_precomputedbins_dev(long long numBands, long long nobj, double* Kinterp,
+                                       long long ld, const double* v1s, const double* v2s,
+                                       const long long* p1s, const long long* p2s,
+                                       const double* grid1, const double* grid2,
+                                       const double* Kgrid, long long n1, long long n2,
+                                       void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Batched / fused entry points used by the new host path (device pointers only).
  * ---------------------------------------------------------------------------------------- */

@@ -222,6 +222,20 @@ def kernel_parts_interp(NO1, NO2, Kinterp, b1, fz1, p1s, b2, fz2, p2s, fzGrid, K
 # ------------------------------------------------------------------------------------------------
 # NumPy restatements of the Python-level algebra
 # ------------------------------------------------------------------------------------------------
+def bilininterp_precomputedbins(numBands, nobj, Kinterp, v1s, v2s, p1s, p2s, grid1, grid2, Kgrid):
+    """delight/utils_cy.pyx:25-50 (NumPy restatement)."""
+    p1, p2 = np.asarray(p1s[:nobj]), np.asarray(p2s[:nobj])
+    v1, v2 = np.asarray(v1s[:nobj]), np.asarray(v2s[:nobj])
+    dzm2 = 1. / (grid1[p1 + 1] - grid1[p1]) / (grid2[p2 + 1] - grid2[p2])
+    for b in range(numBands):
+        G = Kgrid[b]
+        Kinterp[b, :nobj] = dzm2 * (
+            (grid1[p1 + 1] - v1) * (grid2[p2 + 1] - v2) * G[p1, p2]
+            + (v1 - grid1[p1]) * (grid2[p2 + 1] - v2) * G[p1 + 1, p2]
+            + (grid1[p1 + 1] - v1) * (v2 - grid2[p2]) * G[p1, p2 + 1]
+            + (v1 - grid1[p1]) * (v2 - grid2[p2]) * G[p1 + 1, p2 + 1])
+
+
 def approx_DL(z):
     """delight/utils.py:12-13."""
     return np.exp(30.5 * np.asarray(z, dtype=float) ** 0.04 - 21.7)

@@ -1335,3 +1335,27 @@ def test_apply_fused_to_host_matches_apply_fused(golden, sdss):
     n = g["pdfs"].shape[0]
     np.testing.assert_allclose(host["pdf"].numpy()[:n], g["pdfs"], rtol=RTOL,
                                atol=1e-290 * g["pdfs"].max())
+
+
+def test_bilininterp_precomputedbins_vs_oracle(orc):
+    """utils_cy.bilininterp_precomputedbins (utils_cy.pyx:25-50; the reference's tests/test_utils.py
+    shapes): the Python shim and the raw host ABI against the oracle."""
+    from delight_b200 import _lib
+    from delight_b200.utils_cy import bilininterp_precomputedbins, find_positions
+    rng = np.random.default_rng(0)
+    numBands, nobj, nz1, nz2 = 3, 10, 40, 50
+    grid1, grid2 = np.logspace(0., 1., nz1), np.linspace(1., 10., nz2)
+    v1s, v2s = rng.uniform(1, 10, nobj), rng.uniform(1, 10, nobj)
+    p1s, p2s = np.zeros(nobj, dtype=np.int64), np.zeros(nobj, dtype=np.int64)
+    find_positions(nobj, nz1, v1s, p1s, grid1)
+    find_positions(nobj, nz2, v2s, p2s, grid2)
+    Kgrid = np.stack([(grid1[:, None] * grid2[None, :]) ** (b + 1.) for b in range(numBands)])
+    want, got, raw = (np.zeros((numBands, nobj)) for _ in range(3))
+    orc.bilininterp_precomputedbins(numBands, nobj, want, v1s, v2s, p1s, p2s, grid1, grid2, Kgrid)
+    bilininterp_precomputedbins(numBands, nobj, got, v1s, v2s, p1s, p2s, grid1, grid2, Kgrid)
+    np.testing.assert_allclose(got, want, rtol=1e-13)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    _lib.check(_lib.lib().dl_bilininterp_precomputedbins_host(
+        numBands, nobj, P(raw), P(v1s), P(v2s), P(p1s), P(p2s), P(grid1), P(grid2), P(Kgrid),
+        nz1, nz2))
+    np.testing.assert_allclose(raw, want, rtol=1e-13)

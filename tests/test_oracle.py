@@ -258,3 +258,30 @@ def test_compressed_second_pass_matches_reference_twin(golden):
     # duplicate and out-of-range stored indices select fewer columns
     assert (g["sel_n0"][1] >= 0).sum() == g["indices"].shape[1] - 1
     assert (g["sel_n0"][2] >= 0).sum() == g["indices"].shape[1] - 1
+
+
+def test_bilininterp_precomputedbins_matches_compiled_reference():
+    """utils_cy.pyx:25-50 restated in NumPy against the compiled reference on the shapes of the
+    reference's own tests/test_utils.py:89-115 (skipped where oracle/_ref is not built)."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    ref.load()
+    from delight.utils_cy import bilininterp_precomputedbins as cy, find_positions
+    rng = np.random.default_rng(0)
+    numBands, nobj, nz1, nz2 = 3, 10, 40, 50
+    grid1, grid2 = np.logspace(0., 1., nz1), np.linspace(1., 10., nz2)
+    v1s, v2s = rng.uniform(1, 10, nobj), rng.uniform(1, 10, nobj)
+    p1s, p2s = np.zeros(nobj, dtype=np.int64), np.zeros(nobj, dtype=np.int64)
+    find_positions(nobj, nz1, v1s, p1s, grid1)
+    find_positions(nobj, nz2, v2s, p2s, grid2)
+    Kgrid = np.stack([(grid1[:, None] * grid2[None, :]) ** (b + 1.) for b in range(numBands)])
+    want, got = np.zeros((numBands, nobj)), np.zeros((numBands, nobj))
+    cy(numBands, nobj, want, v1s, v2s, p1s, p2s, grid1, grid2, Kgrid)
+    orc.bilininterp_precomputedbins(numBands, nobj, got, v1s, v2s, p1s, p2s, grid1, grid2, Kgrid)
+    np.testing.assert_allclose(got, want, rtol=1e-13)
+    # and it interpolates: exact on a bilinear function
+    Kb = (grid1[:, None] + 2 * grid2[None, :])[None]
+    out = np.zeros((1, nobj))
+    orc.bilininterp_precomputedbins(1, nobj, out, v1s, v2s, p1s, p2s, grid1, grid2, Kb)
+    np.testing.assert_allclose(out[0], v1s + 2 * v2s, rtol=1e-13)
