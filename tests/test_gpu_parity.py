@@ -1359,3 +1359,83 @@ def test_bilininterp_precomputedbins_vs_oracle(orc):
         numBands, nobj, P(raw), P(v1s), P(v2s), P(p1s), P(p2s), P(grid1), P(grid2), P(Kgrid),
         nz1, nz2))
     np.testing.assert_allclose(raw, want, rtol=1e-13)
+
+
+@pytest.mark.parametrize("nO,nT,nz,nB,nf,het,zdep,K,want_evid", [
+    (37, 45, 131, 6, 6, False, False, 7, True),      # nothing a multiple of the tile sizes
+    (37, 45, 131, 6, 6, False, True, 7, False),      # evidences in the workspace only
+    (70, 33, 65, 7, 4, True, False, 5, True),        # per-target band lists
+    (5, 70, 257, 16, 16, False, False, 0, True),     # 16 warps x 64 z, no top-K
+    (33, 40, 129, 28, 21, False, True, 40, False),   # K = nT
+])
+def test_fused_writes_stay_inside_their_buffers(nO, nT, nz, nB, nf, het, zdep, K, want_evid):
+    """Guard bands (compute-sanitizer is not available on the GPU pool): every output of
+    dl_like_fused_dev and its workspace -- sized exactly as dl_fused_workspace_bytes says -- are
+    carved out of ONE arena filled with a sentinel, 512 bytes apart.  After the call the gaps
+    must be untouched, and the results must equal those of apply_fused on its own buffers."""
+    import torch
+    from delight_b200 import _lib, apply
+    rng = np.random.default_rng(nO + nT)
+    zgrid = np.linspace(0.01, 3.0, nz)
+    mm = rng.uniform(0.5, 2.0, (nz, nT, nB)) * 1e5
+    mc = (mm * rng.uniform(1e-3, 5e-2, (nz, nT, nB))) ** 2
+    bands = np.tile(np.arange(nB), (nO, 1))
+    if het:
+        for o in range(nO):
+            bands[o, :nf] = np.sort(rng.choice(nB, nf, replace=False))
+    nfs = np.full(nO, nf)
+    fl = np.zeros((nO, nB)); fv = np.zeros((nO, nB))
+    for o in range(nO):
+        true = mm[rng.integers(nz), rng.integers(nT), bands[o, :nf]] * 4e-10
+        fv[o, :nf] = (0.05 * true) ** 2
+        fl[o, :nf] = true * (1 + 0.05 * rng.standard_normal(nf))
+    grid = apply.ModelGrid.from_legacy(mm, mc)
+    prior = grid.gaussian_prior(zgrid, rng.uniform(0.01, 3.0, nT), 0.5)
+    t = apply.Targets(fl, fv, bands, nfs)
+    eh = rng.uniform(0.5, 2, nz) if zdep else 1.0
+    ev = rng.uniform(0.1, 0.5, nz) if zdep else 0.25
+    want = apply.apply_fused(grid, prior, zgrid, t, ell_hat=eh, ell_var=ev, K=K,
+                             want_evid=want_evid)
+
+    L = _lib.lib()
+    ext = int(want_evid or K == 0)
+    wsb = int(L.dl_fused_workspace_bytes(nO, nT, nz, ext))
+    GAP = 512
+    sizes = dict(pdf=nO * nz * 8, evid=nO * nT * 8 if want_evid else 0, top_idx=nO * K * 8,
+                 top_ev=nO * K * 8, ws=wsb)
+    off, cur = {}, GAP
+    for name, nb in sizes.items():
+        off[name] = cur
+        cur = (cur + nb + GAP + 255) // 256 * 256
+    arena = torch.full((cur + GAP,), 0xA5, dtype=torch.uint8, device="cuda")
+    base = arena.data_ptr()
+    assert base % 256 == 0
+    P = lambda name: ctypes.c_void_p(base + off[name]) if sizes[name] else None
+    groups = list(t.launch_groups(per_band_set=zdep))
+    assert len(groups) == 1
+    key, gnf, union, rows, idx = groups[0]
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    obs, var, zg = dev(fl[:, :nf]), dev(fv[:, :nf]), dev(zgrid)
+    drows = dev(rows) if rows is not None else None
+    deh = dev(np.asarray(eh)) if zdep else None
+    dev_ = dev(np.asarray(ev)) if zdep else None
+    _lib.check(L.dl_like_fused_dev(
+        nO, nT, nz, nB, gnf, len(union), (ctypes.c_int * len(union))(*union),
+        _lib.ptr(drows), _lib.ptr(obs), _lib.ptr(var), _lib.ptr(grid.grid), _lib.ptr(prior),
+        _lib.ptr(zg), 1.0 if zdep else float(eh), 1.0 if zdep else float(ev), _lib.ptr(deh),
+        _lib.ptr(dev_), 1.0, K, P("pdf"), nz, P("evid"), P("top_idx"), P("top_ev"), P("ws"), wsb,
+        _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    host = arena.cpu().numpy()
+    inside = np.zeros(host.size, dtype=bool)
+    for name, nb in sizes.items():
+        inside[off[name]:off[name] + nb] = True
+    assert (host[~inside] == 0xA5).all(), "a kernel wrote outside its buffer"
+    view = lambda name, dt, shape: host[off[name]:off[name] + sizes[name]].view(dt).reshape(shape)
+    # (the PDF rows are sums of atomics: equal up to the order of the additions)
+    np.testing.assert_allclose(view("pdf", np.float64, (nO, nz)), want["pdf"], rtol=1e-12)
+    if want_evid:
+        np.testing.assert_allclose(view("evid", np.float64, (nO, nT)), want["evid"], rtol=1e-12)
+    if K:
+        np.testing.assert_array_equal(view("top_idx", np.int64, (nO, K)), want["top_idx"])
+        np.testing.assert_allclose(view("top_ev", np.float64, (nO, K)), want["top_ev"], rtol=1e-12)

@@ -91,6 +91,27 @@ def test_dropin_signatures_and_dtype_errors():
         utils_cy.find_positions(2, 3, np.ones((2, 1)), np.zeros(2, dtype=np.int64), np.ones(3))
 
 
+def test_bilininterp_shim_checks_its_arguments_before_touching_the_device():
+    """utils_cy.pyx:25-50 indexes without bounds checks; the shim refuses inconsistent shapes and
+    bins outside the grids (and treats empty inputs as a no-op) before any device work."""
+    import inspect
+    sig = inspect.signature(utils_cy.bilininterp_precomputedbins)
+    assert list(sig.parameters) == ["numBands", "nobj", "Kinterp", "v1s", "v2s", "p1s", "p2s",
+                                    "grid1", "grid2", "Kgrid"]
+    g1, g2 = np.linspace(0., 1., 4), np.linspace(0., 1., 5)
+    K = np.ones((2, 4, 5))
+    out = np.zeros((2, 3))
+    v = np.full(3, 0.5)
+    p = np.ones(3, dtype=np.int64)
+    utils_cy.bilininterp_precomputedbins(2, 0, out, v, v, p, p, g1, g2, K)        # no-op
+    with pytest.raises(ValueError, match="inconsistent"):
+        utils_cy.bilininterp_precomputedbins(3, 3, out, v, v, p, p, g1, g2, K)    # 3 bands > 2
+    with pytest.raises(ValueError, match="bin positions"):
+        utils_cy.bilininterp_precomputedbins(2, 3, out, v, v, p + 2, p, g1, g2, K)
+    with pytest.raises(ValueError, match="dtype mismatch"):
+        utils_cy.bilininterp_precomputedbins(2, 3, out, v, v, p.astype(np.int32), p, g1, g2, K)
+
+
 def test_no_cpu_fallback_without_device():
     import torch
     if torch.cuda.is_available():
