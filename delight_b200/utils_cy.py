@@ -95,7 +95,10 @@ def _dev(a):
 def _dev_out(a):
     """Device copy of an array the kernel will WRITE to (never shared with the cache)."""
     torch = _lib.require_cuda()
-    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    h = torch.from_numpy(np.ascontiguousarray(a))
+    d = torch.empty(h.shape, dtype=h.dtype, device="cuda")
+    d.copy_(h)
+    return d
 
 
 def approx_flux_likelihood_cy(like, nz, nt, nf, f_obs, f_obs_var, f_mod, f_mod_covar,

@@ -1439,3 +1439,23 @@ def test_fused_writes_stay_inside_their_buffers(nO, nT, nz, nB, nf, het, zdep, K
     if K:
         np.testing.assert_array_equal(view("top_idx", np.int64, (nO, K)), want["top_idx"])
         np.testing.assert_allclose(view("top_ev", np.float64, (nO, K)), want["top_ev"], rtol=1e-12)
+
+
+def test_guard_bands_are_active_and_catch_a_stray_write(guard_bands):
+    """The suite's own bounds check (tests/conftest.py): allocations of the host layer sit inside
+    sentinel bands, and a write one element past the end is reported."""
+    import torch
+    from delight_b200.utils_cy import find_positions
+    t = torch.empty((3, 5), dtype=torch.float64, device="cuda")
+    flat, nbytes, shape = guard_bands.records[-1]
+    assert nbytes == 120 and shape == (3, 5)
+    assert t.data_ptr() == flat.data_ptr() + guard_bands.size
+    n0 = len(guard_bands.records)
+    p = np.zeros(4, dtype=np.int64)
+    find_positions(4, 6, np.array([0.5, 1.5, 2.5, 4.5]), p, np.arange(6.))
+    assert len(guard_bands.records) > n0          # the shim's device buffers are guarded too
+    guard_bands.check()
+    t.view(-1).as_strided((16,), (1,))[15] = 1.0  # one element past the end of `t`
+    with pytest.raises(AssertionError, match="wrote outside"):
+        guard_bands.check()
+    flat[guard_bands.size + nbytes:].fill_(0xA5)
