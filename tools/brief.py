@@ -1,6 +1,8 @@
 import sys, json
 last_dbg=None
-for line in sys.stdin:
+# usage: brief.py FILE   or   ... | brief.py   (never waits on a terminal)
+src = open(sys.argv[1]) if len(sys.argv) > 1 else sys.stdin
+for line in src:
     line=line.strip()
     if line.startswith('[dbgwait]'):
         last_dbg=line
