@@ -70,6 +70,21 @@ constexpr int ZJ = 2;         // redshifts a lane processes jointly (independent
 #ifndef DL_TAILPAIR
 #define DL_TAILPAIR 2
 #endif
+#ifndef DL_MONT
+#define DL_MONT 1             // band pairs share reciprocals (Montgomery's trick, up to BIGNF bands)
+#endif
+#ifndef DL_MONT_GROUP
+#define DL_MONT_GROUP 2       // at most this many factors share a reciprocal (model in registers)
+#endif
+#ifndef DL_MONT_GROUP_S
+#define DL_MONT_GROUP_S 2     // the same with the model values read from the stage
+#endif
+#ifndef DL_MONT_TJ2
+#define DL_MONT_TJ2 0         // ... also where two targets are evaluated jointly (8 bands)
+#endif
+#ifndef DL_MONT_ROLL
+#define DL_MONT_ROLL 1        // beyond BIGNF bands: two band pairs share a reciprocal
+#endif
 #ifndef DL_TJ2_NF
 #define DL_TJ2_NF 8
 #endif
@@ -145,6 +160,7 @@ __host__ __device__ inline size_t fused_smem_bytes(int cfg, int nf, bool het, bo
 // rows differ from target to target).
 template <int NF>
 struct RegModel {
+    static constexpr bool kInRegs = true;
     const double (&mm)[ZJ][NF];
     const double (&cc)[ZJ][NF];
     __device__ __forceinline__ double m(int c, int f) const { return mm[c][f]; }
@@ -154,6 +170,7 @@ struct RegModel {
 // RegModel, which makes room for two targets jointly (DL_HYBRID)
 template <int NF, int FZC>
 struct HybridModel {
+    static constexpr bool kInRegs = true;
     const double (&mm)[ZJ][NF];
     const double* stz;      // stage + the lane's first redshift
     __device__ __forceinline__ double m(int c, int f) const { return mm[c][f]; }
@@ -161,12 +178,14 @@ struct HybridModel {
 };
 template <int NF, int FZC>
 struct SmemModel {
+    static constexpr bool kInRegs = false;
     const double* stz;      // stage + the lane's first redshift
     __device__ __forceinline__ double m(int c, int f) const { return stz[f * FZC + 32 * c]; }
     __device__ __forceinline__ double cv(int c, int f) const { return stz[(NF + f) * FZC + 32 * c]; }
 };
 template <int NF, int FZC>
 struct SmemModelHet {
+    static constexpr bool kInRegs = false;
     const double* stz;      // stage + the lane's first redshift
     const int* off;         // the target's NF row offsets (elements) into a stage
     int var0;               // nU * FZC: first variance row
@@ -263,10 +282,114 @@ __device__ __forceinline__ void cells_xy(const double* const (&tcs)[TJ], const M
             }
         }
     };
+    if constexpr (!ROLL && DL_MONT && (TJ == 1 || DL_MONT_TJ2)) {
+        // ONE reciprocal per cell (Montgomery's trick over the pair products q_i, and the odd
+        // band): the prefix products are the determinant anyway, 1/q_i = (prod_{k<i} q_k) *
+        // (prod_{k>i} q_k) / prod_k q_k.  n factors: 2 (n - 1) multiplications instead of
+        // n - 1 reciprocals (3 FP64 + MUFU + 1 move each).
+        constexpr int NP = NF / 2, NQ = NP + (NF & 1);
+        // factors per reciprocal: with the model in registers two (three keep 12 more doubles
+        // alive across the reciprocal and spill: 1.131 s against 1.071 s at 6 bands)
+        constexpr int MGW = Model::kInRegs ? DL_MONT_GROUP : DL_MONT_GROUP_S;
+        constexpr int MG = MGW < NQ ? MGW : NQ;
+#pragma unroll
+        for (int j = 0; j < TJ; ++j) {
+#pragma unroll
+            for (int g0 = 0; g0 < NQ; g0 += MG) {
+                const int n = (NQ - g0) < MG ? (NQ - g0) : MG;          // factors g0 .. g0 + n - 1
+                double v[ZJ][2 * MG], q[ZJ][MG], pre[ZJ][MG], R[ZJ], inv[ZJ][MG];
+#pragma unroll
+                for (int i = 0; i < n; ++i) {
+                    const bool odd = (g0 + i) == NP;                    // the unpaired last band
+                    const int f = 2 * (g0 + i);
+#pragma unroll
+                    for (int c = 0; c < ZJ; ++c) {
+                        v[c][2 * i] = fma(e2[j][c], md.cv(c, f), tc1[j][f].x);
+                        if (!odd) {
+                            v[c][2 * i + 1] = fma(e2[j][c], md.cv(c, f + 1), tc1[j][f + 1].x);
+                            q[c][i] = v[c][2 * i] * v[c][2 * i + 1];
+                        } else {
+                            q[c][i] = v[c][2 * i];
+                        }
+                        pre[c][i] = i ? pre[c][i - 1] * q[c][i] : q[c][i];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < ZJ; ++c) {
+                    P[j][c] *= pre[c][n - 1];
+                    R[c] = rcp_fast(pre[c][n - 1]);
+                }
+#pragma unroll
+                for (int i = n - 1; i >= 1; --i)
+#pragma unroll
+                    for (int c = 0; c < ZJ; ++c) {
+                        inv[c][i] = pre[c][i - 1] * R[c];
+                        R[c] *= q[c][i];
+                    }
+#pragma unroll
+                for (int c = 0; c < ZJ; ++c) inv[c][0] = R[c];
+#pragma unroll
+                for (int i = 0; i < n; ++i) {
+                    const bool odd = (g0 + i) == NP;
+                    const int f = 2 * (g0 + i);
+                    if (!odd) {
+                        const double oa = tc1[j][f].y, ob = tc1[j][f + 1].y;
+#pragma unroll
+                        for (int c = 0; c < ZJ; ++c) {
+                            acc(j, c, f, md.m(c, f), v[c][2 * i + 1] * inv[c][i], oa);
+                            acc(j, c, f + 1, md.m(c, f + 1), v[c][2 * i] * inv[c][i], ob);
+                        }
+                    } else {
+                        const double oa = tc1[j][f].y;
+#pragma unroll
+                        for (int c = 0; c < ZJ; ++c) acc(j, c, f, md.m(c, f), inv[c][i], oa);
+                    }
+                }
+            }
+        }
+    } else {
+    // four bands (two pairs) on one reciprocal: 1/q_a = q_b / (q_a q_b)
+    auto pair2 = [&](int f, double (&Pd)[TJ][ZJ]) {
+#pragma unroll
+        for (int j = 0; j < TJ; ++j) {
+            double v[ZJ][4], R[ZJ], ia[ZJ], ib[ZJ];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double vo = tc1[j][f + i].x;
+#pragma unroll
+                for (int c = 0; c < ZJ; ++c) v[c][i] = fma(e2[j][c], md.cv(c, f + i), vo);
+            }
+#pragma unroll
+            for (int c = 0; c < ZJ; ++c) {
+                const double qa = v[c][0] * v[c][1], qb = v[c][2] * v[c][3];
+                const double qq = qa * qb;
+                R[c] = rcp_fast(qq);
+                ia[c] = qb * R[c]; ib[c] = qa * R[c];
+                Pd[j][c] *= qq;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double ob = tc1[j][f + i].y;
+#pragma unroll
+                for (int c = 0; c < ZJ; ++c)
+                    acc(j, c, f + i, md.m(c, f + i), v[c][i ^ 1] * (i < 2 ? ia[c] : ib[c]), ob);
+            }
+        }
+    };
+    if constexpr (ROLL && DL_MONT_ROLL) {
+        constexpr int A4 = F0 & ~3, B4 = F0 + ((NG - F0) & ~3);
+#pragma unroll 1
+        for (int f = 0; f < A4; f += 4) pair2(f, P);
+        if (A4 < F0) pair(A4, P);
+#pragma unroll 1
+        for (int f = F0; f < B4; f += 4) pair2(f, P2);
+        if (B4 < NG) pair(B4, P2);
+    } else {
 #pragma unroll (ROLL ? BAND_UNROLL1 : NF)
     for (int f = 0; f < F0; f += 2) pair(f, P);
 #pragma unroll (ROLL ? BAND_UNROLL1 : NF)
     for (int f = F0; f < NG; f += 2) pair(f, P2);
+    }
     if (NF - NG == 1) {
         constexpr int f = NF - 1;
         double ma[ZJ], ca[ZJ];
@@ -282,6 +405,7 @@ __device__ __forceinline__ void cells_xy(const double* const (&tcs)[TJ], const M
                 if (NF > BIGNF) P2[j][c] *= var; else P[j][c] *= var;
             }
         }
+    }
     }
     // chi2 and (det)^-1/2 (utils_cy.pyx:111-118)
 #pragma unroll

@@ -7,6 +7,8 @@ import sys
 import numpy as np
 import torch
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
 from delight_b200 import _lib, apply
 
 nO, nT = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (2048, 1500)
