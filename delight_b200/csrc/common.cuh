@@ -108,7 +108,7 @@ constexpr int EXP_TAB = 1 << DL_EXPTAB_BITS;
 __device__ __forceinline__ void exp_tab_init(double* tab, int tid, int nthreads) {
     for (int j = tid; j < EXP_TAB; j += nthreads) tab[j] = exp2((double)j / EXP_TAB);
 }
-__device__ __forceinline__ double exp_nonpos_tab(double x, const double* tab) {
+__device__ __forceinline__ double exp_nonpos_tab(double x, const double* tab, bool zero = false) {
     const double L2EN = 1.4426950408889634074 * EXP_TAB;           // N / ln 2
     const double LN2N = 6.93147180559945286227e-01 / EXP_TAB;      // ln 2 / N (exact scaling)
     const double SHIFT = 6755399441055744.0;                       // 1.5 * 2^52
@@ -132,7 +132,8 @@ __device__ __forceinline__ double exp_nonpos_tab(double x, const double* tab) {
     // so n = 0, the exponent is left alone and p (= NaN) comes back as it is.
     const unsigned hx = (unsigned)__double2hiint(x);
     const bool under = hx - 0xC0862000u <= 0xFFF00000u - 0xC0862000u;     // -708 >= x >= -inf
-    return under ? 0.0 : res;
+    // `zero`: the caller's own reason for a 0 (a padded cell), folded into the same select
+    return (under || zero) ? 0.0 : res;
 }
 
 __device__ __forceinline__ double warp_max(double v) {

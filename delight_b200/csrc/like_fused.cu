@@ -49,6 +49,10 @@ __global__ void prep_targets_kernel(int nO, int NF, int TCS, int fzc,
     for (int f = 0; f < NF; ++f) s += log2(var[(size_t)o * NF + f]);
     int k = (int)rint(s / NF);
     k = k < -1000 ? -1000 : (k > 1000 ? 1000 : k);
+#if DL_HCFOLD
+    k |= 1;                                    // odd: h = sqrt(1 / (2 c)) is a power of two
+    const double h = ldexp(1.0, -(k + 1) / 2);
+#endif
     const double c = ldexp(1.0, k), ic = ldexp(1.0, -k);
     const double sic = sqrt(ic * cov_scale);   // ell^2 * (cov_scale * model variance) / c
     for (int f = 0; f < NF; ++f) {
@@ -58,8 +62,13 @@ __global__ void prep_targets_kernel(int nO, int NF, int TCS, int fzc,
         tc[2 * f] = ob * w * sic;       // pass-0 weights carry sqrt(ic cov_scale): e2 = (FOT'/FTT)^2
         tc[2 * f + 1] = w;
         tc[2 * NF + 2 * f] = vs;
+#if DL_HCFOLD
+        tc[2 * NF + 2 * f + 1] = ob * h;
+        tc[4 * NF + f] = -(ob * h) * (ob * h);
+#else
         tc[2 * NF + 2 * f + 1] = ob;
         tc[4 * NF + f] = ob * ob;
+#endif
     }
     double* tk = tc + 5 * NF;
     tk[TC_HC] = -0.5 * ic;
@@ -71,6 +80,11 @@ __global__ void prep_targets_kernel(int nO, int NF, int TCS, int fzc,
     tk[TC_CS] = c * sic;                              // z-dependent ell priors: pOT0 = cs * zot
     tk[TC_XOFF] = 0.0;
     tk[TC_SPARE] = 0.0;
+#if DL_HCFOLD
+    tk[TC_POT] *= h;
+    tk[TC_SPARE] = c * h;                             // z-dependent ell priors: pOT = (c h) * zot
+    tk[TC_POO] = tk[TC_POO0] = -0.5 * (ell_hat * ell_hat / ell_var);     // (c h_c = -1/2)
+#endif
     if (rows != nullptr) {
         int* off = reinterpret_cast<int*>(tk + TC_NCONST);
         for (int f = 0; f < NF; ++f) off[f] = rows[(size_t)o * NF + f] * fzc;
@@ -100,11 +114,15 @@ __global__ void anchor_fold_kernel(int nO, int NF, int TCS, double* __restrict__
         if (mine) {
             double A = Akey[o] ? key_to_double(Akey[o]) : 0.0;
             if (!(fabs(A) <= 1.79769313486231570815e308)) A = 0.0;
+#if DL_HCFOLD
+            tk[TC_POO] = tk[TC_POO0] - A;
+#else
             tk[TC_POO] = tk[TC_POO0] - A / tk[TC_HC];
+#endif
             tk[TC_XOFF] = -A;
             if (rescue) Vbits[o] = 0ull;
         } else {
-            tk[TC_POO] = INFINITY;
+            tk[TC_POO] = DL_HCFOLD ? -INFINITY : INFINITY;
             tk[TC_XOFF] = -INFINITY;
         }
     }

@@ -70,6 +70,12 @@ constexpr int ZJ = 2;         // redshifts a lane processes jointly (independent
 #ifndef DL_TAILPAIR
 #define DL_TAILPAIR 2
 #endif
+#ifndef DL_HCFOLD
+#define DL_HCFOLD 1           // -1/2 and the unit of the variances folded into the target constants
+#endif
+#ifndef DL_PRW
+#define DL_PRW 1              // evidence accumulated as v * (prior * weight)
+#endif
 #ifndef DL_MONT
 #define DL_MONT 1             // band pairs share reciprocals (Montgomery's trick, up to BIGNF bands)
 #endif
@@ -114,6 +120,11 @@ __host__ __device__ constexpr int cfg_tt(int cfg) { return 32; }                
 //   [0, 2NF)      (a_f s, w_f)          pass 0:  a = obs / var', w = 1 / var'
 //   [2NF, 4NF)    (var'_f, obs_f)       pass 1
 //   [4NF, 5NF)    obs_f^2
+// DL_HCFOLD: c is an ODD power of two, so that h = sqrt(1 / (2 c)) is a power of two as well, and
+//   the pass-1 constants hold (var'_f, h obs_f), -(h obs_f)^2, TC_POT = h x, TC_POO = -x / (2 c)
+//   - anchor: the sums come out as FOT' = h FOT and FOO'' = -FOO / (2 c) - A, and
+//   x = -chi2 / (2 c) - A = FOT'^2 / FTT + FOO'' is one FMA behind FOT'^2 (no h_c multiplication,
+//   no mask addition: padded cells are zeroed in the select of the exponential).
 //   5NF + TC_*    scalars below
 //   then (per-target band lists only) NF int32 element offsets of the target's band rows in a stage
 enum { TC_HC = 0, TC_POT0, TC_POT, TC_PTT, TC_POO, TC_C, TC_CS, TC_XOFF, TC_POO0, TC_SPARE, TC_NCONST };
@@ -196,7 +207,7 @@ struct SmemModelHet {
 // TJ targets are evaluated jointly against the same ZJ cells: every model value is read once
 // for all of them (with the model in shared memory that halves the dominant LDS traffic) and
 // every statement carries TJ x ZJ independent dependency chains.
-template <int NF, int TJ, class Model>
+template <int NF, int TJ, bool ADDMASK, class Model>
 __device__ __forceinline__ void cells_xy(const double* const (&tcs)[TJ], const Model md,
                                          const double (&pOT0)[TJ][ZJ], const double (&pOT)[TJ][ZJ],
                                          const double (&pTT)[TJ][ZJ], const double (&pOO)[TJ][ZJ],
@@ -424,6 +435,11 @@ __device__ __forceinline__ void cells_xy(const double* const (&tcs)[TJ], const M
                 y[j][c] = rsqrt_fast(P[j][c] * ftt[j][c]);
                 rF = (y[j][c] * y[j][c]) * P[j][c];               // 1 / FTT
             }
+#if DL_HCFOLD
+            (void)hc;
+            x[j][c] = fma(fot[j][c] * fot[j][c], rF, foo[j][c]);
+            if (ADDMASK) x[j][c] += xmask[j][c];
+#else
 #if DL_CHI2_EARLY
             // FOT^2 does not wait for 1/FTT: one dependent operation less behind the rsqrt
             const double chi2 = fma(-(fot[j][c] * fot[j][c]), rF, foo[j][c]);
@@ -431,6 +447,7 @@ __device__ __forceinline__ void cells_xy(const double* const (&tcs)[TJ], const M
             const double chi2 = fma(-(fot[j][c] * rF), fot[j][c], foo[j][c]);
 #endif
             x[j][c] = fma(hc, chi2, xmask[j][c]);     // -chi2/2 - A in the target's units
+#endif
         }
     }
 }
@@ -636,11 +653,16 @@ fused_like_kernel(const FusedParams p) {
                 }
             }
             double pr[ZJ], wzv[ZJ], xmask[ZJ], zot[ZJ], ztt[ZJ], zoo[ZJ], zev[ZJ];
+            bool pad[ZJ];
 #pragma unroll
             for (int c = 0; c < ZJ; ++c) {
                 pr[c] = st[2 * var0 + zl + 32 * c];
                 wzv[c] = st[2 * var0 + FZC + zl + 32 * c];
+#if DL_PRW
+                wzv[c] *= pr[c];
+#endif
                 // padded redshifts get x = -inf: they never count for the max and contribute 0
+                pad[c] = DL_HCFOLD && (z0 + zl + 32 * c) >= p.nz;
                 xmask[c] = ((z0 + zl + 32 * c) < p.nz) ? 0.0 : -INFINITY;
                 zot[c] = ztt[c] = zoo[c] = 0.0; zev[c] = 1.0;
                 if (ZDEP) {
@@ -671,9 +693,16 @@ fused_like_kernel(const FusedParams p) {
                             if (ZDEP) {
                                 const double cc = tk[TC_C];
                                 pOT0[j][c] = tk[TC_CS] * zot[c];
+#if DL_HCFOLD
+                                // (TC_SPARE = c h, c h_c = -1/2; the anchor rides on FOO'')
+                                pOT[j][c] = tk[TC_SPARE] * zot[c]; pTT[j][c] = cc * ztt[c];
+                                pOO[j][c] = SAMPLE ? -0.5 * zoo[c] : fma(-0.5, zoo[c], tk[TC_XOFF]);
+                                xm[j][c] = xmask[c];
+#else
                                 pOT[j][c] = cc * zot[c]; pTT[j][c] = cc * ztt[c];
                                 pOO[j][c] = cc * zoo[c];
                                 xm[j][c] = SAMPLE ? xmask[c] : xmask[c] + tk[TC_XOFF];   // -A
+#endif
                             } else {
                                 // the anchor is folded into the constant term of FOO (TC_POO);
                                 // the sampling pass measures the un-anchored exponent (TC_POO0)
@@ -685,18 +714,18 @@ fused_like_kernel(const FusedParams p) {
                         }
                     }
                     if constexpr (HET)
-                        cells_xy<NF, TJ>(tcs, SmemModelHet<NF, FZC>{st + zl,
+                        cells_xy<NF, TJ, SAMPLE || !DL_HCFOLD>(tcs, SmemModelHet<NF, FZC>{st + zl,
                                              reinterpret_cast<const int*>(tcs[0] + 5 * NF + TC_NCONST),
                                              var0},
                                          pOT0, pOT, pTT, pOO, zev, xm, xg, yg);
                     else if constexpr (SMODEL)
-                        cells_xy<NF, TJ>(tcs, SmemModel<NF, FZC>{st + zl}, pOT0, pOT, pTT, pOO,
+                        cells_xy<NF, TJ, SAMPLE || !DL_HCFOLD>(tcs, SmemModel<NF, FZC>{st + zl}, pOT0, pOT, pTT, pOO,
                                          zev, xm, xg, yg);
                     else if constexpr (HYBRID)
-                        cells_xy<NF, TJ>(tcs, HybridModel<NF, FZC>{m, st + zl}, pOT0, pOT, pTT, pOO,
+                        cells_xy<NF, TJ, SAMPLE || !DL_HCFOLD>(tcs, HybridModel<NF, FZC>{m, st + zl}, pOT0, pOT, pTT, pOO,
                                          zev, xm, xg, yg);
                     else
-                        cells_xy<NF, TJ>(tcs, RegModel<NF>{m, cv}, pOT0, pOT, pTT, pOO, zev, xm,
+                        cells_xy<NF, TJ, SAMPLE || !DL_HCFOLD>(tcs, RegModel<NF>{m, cv}, pOT0, pOT, pTT, pOO, zev, xm,
                                          xg, yg);
 #pragma unroll
                     for (int j = 0; j < TJ; ++j)
@@ -721,7 +750,7 @@ fused_like_kernel(const FusedParams p) {
                         vh[j] = 0;
 #pragma unroll
                         for (int c = 0; c < ZJ; ++c) {
-                            v[j][c] = exp_nonpos_tab(x[j][c], etab) * y[j][c];      // :118,128
+                            v[j][c] = exp_nonpos_tab(x[j][c], etab, pad[c]) * y[j][c];   // :118,128
                             ovf = max(ovf, __double2hiint(x[j][c]));
                             vh[j] = max(vh[j], __double2hiint(v[j][c]));
                         }
@@ -744,9 +773,16 @@ fused_like_kernel(const FusedParams p) {
                     for (int j = 0; j < TP; ++j)
 #pragma unroll
                         for (int c = 0; c < ZJ; ++c) {
+#if DL_PRW
+                            // (wzv holds prior x trapezoid weight: one multiplication less)
+                            double* pd = pdfw + (o + j) * FZC + zl + 32 * c;
+                            *pd = fma(v[j][c], pr[c], *pd);
+                            Eo[j] = fma(v[j][c], wzv[c], Eo[j]);
+#else
                             const double vp = v[j][c] * pr[c];
                             pdfw[(o + j) * FZC + zl + 32 * c] += vp;
                             Eo[j] = fma(vp, wzv[c], Eo[j]);
+#endif
                         }
                 }
 #pragma unroll
