@@ -108,7 +108,10 @@ constexpr int EXP_TAB = 1 << DL_EXPTAB_BITS;
 __device__ __forceinline__ void exp_tab_init(double* tab, int tid, int nthreads) {
     for (int j = tid; j < EXP_TAB; j += nthreads) tab[j] = exp2((double)j / EXP_TAB);
 }
-__device__ __forceinline__ double exp_nonpos_tab(double x, const double* tab, bool zero = false) {
+constexpr unsigned EXP_UNDER = 0xFFF00000u - 0xC0862000u;      // see `under` below
+constexpr unsigned EXP_ZERO = 0xFFFFFFFFu;                    // as `lim`: the result is 0 for every x
+__device__ __forceinline__ double exp_nonpos_tab(double x, const double* tab,
+                                                 unsigned lim = EXP_UNDER) {
     const double L2EN = 1.4426950408889634074 * EXP_TAB;           // N / ln 2
     const double LN2N = 6.93147180559945286227e-01 / EXP_TAB;      // ln 2 / N (exact scaling)
     const double SHIFT = 6755399441055744.0;                       // 1.5 * 2^52
@@ -131,9 +134,9 @@ __device__ __forceinline__ double exp_nonpos_tab(double x, const double* tab, bo
     // every NaN the GPU produces or NumPy hands over has a zero low word (0x7ff8... / 0xfff8...),
     // so n = 0, the exponent is left alone and p (= NaN) comes back as it is.
     const unsigned hx = (unsigned)__double2hiint(x);
-    const bool under = hx - 0xC0862000u <= 0xFFF00000u - 0xC0862000u;     // -708 >= x >= -inf
-    // `zero`: the caller's own reason for a 0 (a padded cell), folded into the same select
-    return (under || zero) ? 0.0 : res;
+    // (`lim` = EXP_ZERO is the caller's own reason for a 0 -- a padded cell -- at no extra cost)
+    const bool under = hx - 0xC0862000u <= lim;                           // -708 >= x >= -inf
+    return under ? 0.0 : res;
 }
 
 __device__ __forceinline__ double warp_max(double v) {

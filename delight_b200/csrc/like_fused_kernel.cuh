@@ -653,7 +653,7 @@ fused_like_kernel(const FusedParams p) {
                 }
             }
             double pr[ZJ], wzv[ZJ], xmask[ZJ], zot[ZJ], ztt[ZJ], zoo[ZJ], zev[ZJ];
-            bool pad[ZJ];
+            unsigned pad[ZJ];          // exp_nonpos_tab's limit: EXP_ZERO for padded redshifts
 #pragma unroll
             for (int c = 0; c < ZJ; ++c) {
                 pr[c] = st[2 * var0 + zl + 32 * c];
@@ -662,7 +662,7 @@ fused_like_kernel(const FusedParams p) {
                 wzv[c] *= pr[c];
 #endif
                 // padded redshifts get x = -inf: they never count for the max and contribute 0
-                pad[c] = DL_HCFOLD && (z0 + zl + 32 * c) >= p.nz;
+                pad[c] = (DL_HCFOLD && (z0 + zl + 32 * c) >= p.nz) ? EXP_ZERO : EXP_UNDER;
                 xmask[c] = ((z0 + zl + 32 * c) < p.nz) ? 0.0 : -INFINITY;
                 zot[c] = ztt[c] = zoo[c] = 0.0; zev[c] = 1.0;
                 if (ZDEP) {
