@@ -155,3 +155,35 @@ def test_catalogue_reader_matches_reference_parsing(golden, tmp_path):
             np.testing.assert_array_equal(cat.bands[i, :B], g[key + "_bands"][i, :B])
             np.testing.assert_array_equal(cat.fluxes[i, :B], g[key + "_flux"][i, :B])
             np.testing.assert_allclose(cat.fluxes_var[i, :B], g[key + "_var"][i, :B], rtol=1e-15)
+
+
+def test_fused_kernel_binary_properties():
+    """Static checks of the built sm_100a code (cuobjdump, no GPU): every instantiation of the
+    fused kernel fits 128 registers (16 warps per SM in both configurations), and the 6-band main
+    pass is what DESIGN 5.1 says it is -- TMA bulk copies into an mbarrier ring, MUFU-seeded
+    FP64 reciprocals / rsqrt, an FP64 FMA stream with next to no local memory traffic."""
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    lib = _lib.lib_path() if hasattr(_lib, "lib_path") else os.path.join(
+        os.path.dirname(delight_b200.__file__), "libdelight_b200.so")
+    usage = subprocess.run([exe, "--dump-resource-usage", lib], stdout=subprocess.PIPE,
+                           stderr=subprocess.DEVNULL, text=True).stdout
+    regs = [int(m) for m in re.findall(r"fused_like_kernel\S*:\s*\n\s*REG:(\d+)", usage)]
+    assert len(regs) == 32 * 3 * 2          # 1..32 bands x (plain, z-dependent, band lists) x 2 modes
+    assert max(regs) <= 128
+    assert "sm_100a" in usage or "sm_100" in usage
+    name = "_ZN2dl17fused_like_kernelILi6ELb0ELb0ELi0EEEvNS_11FusedParamsE"
+    sass = subprocess.run([exe, "-sass", "-fun", name, lib], stdout=subprocess.PIPE,
+                          stderr=subprocess.DEVNULL, text=True).stdout
+    ops = re.findall(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+(?:\.[A-Z0-9_]+)*)", sass, re.M)
+    count = lambda prefix: sum(1 for o in ops if o.startswith(prefix))
+    assert count("UBLKCP") >= 14            # 6 means + 6 variances + prior + weights per stage
+    assert count("SYNCS") > 0               # mbarrier arrive / try_wait
+    assert count("MUFU.RCP64H") > 0 and count("MUFU.RSQ64H") > 0
+    fp64 = count("DFMA") + count("DMUL") + count("DADD")
+    assert fp64 > 600
+    assert count("LDL") + count("STL") < 0.05 * fp64
+    assert count("DMMA") == count("HMMA") == 0      # nothing here is a dense contraction
