@@ -187,3 +187,32 @@ def test_fused_kernel_binary_properties():
     assert fp64 > 600
     assert count("LDL") + count("STL") < 0.05 * fp64
     assert count("DMMA") == count("HMMA") == 0      # nothing here is a dense contraction
+
+
+def test_c_abi_rejects_bad_arguments_before_any_device_work():
+    """Error convention of include/delight_b200.h: invalid shapes come back as DL_ERR_INVALID with
+    a message from dl_last_error(), decided on the host before anything is launched (so this runs
+    without a GPU).  The reference operators index without checks (boundscheck=False)."""
+    import ctypes
+    L = _lib.lib()
+    ll = ctypes.c_longlong
+    one = (ctypes.c_int * 1)(0)
+    buf = ctypes.create_string_buffer(64)
+    P = ctypes.cast(buf, ctypes.c_void_p)
+
+    def fused(nO=4, nT=5, nz=10, nB=3, nf=3, n_union=3, K=2, ld=10, cov=1.0, ws=P, wsb=64):
+        return L.dl_like_fused_dev(nO, nT, nz, nB, nf, n_union, one, None, P, P, P, P, P, 1.0, 1.0,
+                                   None, None, cov, K, P, ld, None, P, P, ws, wsb, None)
+    cases = [(dict(nf=0), "bands per target"), (dict(nf=33, n_union=33), "bands per target"),
+             (dict(K=6), "K <= min"), (dict(ld=9), "ld_pdf"), (dict(cov=-1.0), "cov_scale"),
+             (dict(n_union=2), "band union"), (dict(nO=0), "bad shape"),
+             (dict(), "workspace too small")]
+    for kw, msg in cases:
+        assert fused(**kw) == 1, kw
+        assert msg in L.dl_last_error().decode(), (kw, L.dl_last_error())
+    assert L.dl_bilininterp_precomputedbins_host(ll(1), ll(1), P, P, P, P, P, P, P, P, ll(1),
+                                                 ll(5)) == 1
+    assert "bad sizes" in L.dl_last_error().decode()
+    assert L.dl_metrics_dev(ll(0), ll(10), P, ll(10), P, None, P, None) == 1
+    assert L.dl_fused_workspace_bytes(ll(64), ll(1000), ll(300), 1) < \
+        L.dl_fused_workspace_bytes(ll(64), ll(1000), ll(300), 0)
