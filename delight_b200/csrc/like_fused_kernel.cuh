@@ -294,10 +294,10 @@ __device__ __forceinline__ void cells_xy(const double* const (&tcs)[TJ], const M
         }
     };
     if constexpr (!ROLL && DL_MONT && (TJ == 1 || DL_MONT_TJ2)) {
-        // ONE reciprocal per cell (Montgomery's trick over the pair products q_i, and the odd
-        // band): the prefix products are the determinant anyway, 1/q_i = (prod_{k<i} q_k) *
-        // (prod_{k>i} q_k) / prod_k q_k.  n factors: 2 (n - 1) multiplications instead of
-        // n - 1 reciprocals (3 FP64 + MUFU + 1 move each).
+        // One reciprocal per GROUP of band pairs (Montgomery's trick over the pair products q_i,
+        // the odd last band being a factor of its own): the prefix products are the determinant
+        // anyway and 1/q_i = (prod_{k<i} q_k) (prod_{k>i} q_k) / prod_k q_k.  n factors: 2 (n - 1)
+        // multiplications instead of n - 1 reciprocals (3 FP64 + MUFU + 1 move each).
         constexpr int NP = NF / 2, NQ = NP + (NF & 1);
         // factors per reciprocal: with the model in registers two (three keep 12 more doubles
         // alive across the reciprocal and spill: 1.131 s against 1.071 s at 6 bands)
@@ -359,64 +359,64 @@ __device__ __forceinline__ void cells_xy(const double* const (&tcs)[TJ], const M
             }
         }
     } else {
-    // four bands (two pairs) on one reciprocal: 1/q_a = q_b / (q_a q_b)
-    auto pair2 = [&](int f, double (&Pd)[TJ][ZJ]) {
+        // four bands (two pairs) on one reciprocal: 1/q_a = q_b / (q_a q_b)
+        auto pair2 = [&](int f, double (&Pd)[TJ][ZJ]) {
 #pragma unroll
-        for (int j = 0; j < TJ; ++j) {
-            double v[ZJ][4], R[ZJ], ia[ZJ], ib[ZJ];
+            for (int j = 0; j < TJ; ++j) {
+                double v[ZJ][4], R[ZJ], ia[ZJ], ib[ZJ];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const double vo = tc1[j][f + i].x;
+                for (int i = 0; i < 4; ++i) {
+                    const double vo = tc1[j][f + i].x;
 #pragma unroll
-                for (int c = 0; c < ZJ; ++c) v[c][i] = fma(e2[j][c], md.cv(c, f + i), vo);
+                    for (int c = 0; c < ZJ; ++c) v[c][i] = fma(e2[j][c], md.cv(c, f + i), vo);
+                }
+#pragma unroll
+                for (int c = 0; c < ZJ; ++c) {
+                    const double qa = v[c][0] * v[c][1], qb = v[c][2] * v[c][3];
+                    const double qq = qa * qb;
+                    R[c] = rcp_fast(qq);
+                    ia[c] = qb * R[c]; ib[c] = qa * R[c];
+                    Pd[j][c] *= qq;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const double ob = tc1[j][f + i].y;
+#pragma unroll
+                    for (int c = 0; c < ZJ; ++c)
+                        acc(j, c, f + i, md.m(c, f + i), v[c][i ^ 1] * (i < 2 ? ia[c] : ib[c]), ob);
+                }
             }
+        };
+        if constexpr (ROLL && DL_MONT_ROLL) {
+            constexpr int A4 = F0 & ~3, B4 = F0 + ((NG - F0) & ~3);
+#pragma unroll 1
+            for (int f = 0; f < A4; f += 4) pair2(f, P);
+            if (A4 < F0) pair(A4, P);
+#pragma unroll 1
+            for (int f = F0; f < B4; f += 4) pair2(f, P2);
+            if (B4 < NG) pair(B4, P2);
+        } else {
+#pragma unroll (ROLL ? BAND_UNROLL1 : NF)
+            for (int f = 0; f < F0; f += 2) pair(f, P);
+#pragma unroll (ROLL ? BAND_UNROLL1 : NF)
+            for (int f = F0; f < NG; f += 2) pair(f, P2);
+        }
+        if (NF - NG == 1) {
+            constexpr int f = NF - 1;
+            double ma[ZJ], ca[ZJ];
 #pragma unroll
-            for (int c = 0; c < ZJ; ++c) {
-                const double qa = v[c][0] * v[c][1], qb = v[c][2] * v[c][3];
-                const double qq = qa * qb;
-                R[c] = rcp_fast(qq);
-                ia[c] = qb * R[c]; ib[c] = qa * R[c];
-                Pd[j][c] *= qq;
-            }
+            for (int c = 0; c < ZJ; ++c) { ma[c] = md.m(c, f); ca[c] = md.cv(c, f); }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const double ob = tc1[j][f + i].y;
+            for (int j = 0; j < TJ; ++j) {
+                const double2 vo = tc1[j][f];
 #pragma unroll
-                for (int c = 0; c < ZJ; ++c)
-                    acc(j, c, f + i, md.m(c, f + i), v[c][i ^ 1] * (i < 2 ? ia[c] : ib[c]), ob);
+                for (int c = 0; c < ZJ; ++c) {
+                    const double var = fma(e2[j][c], ca[c], vo.x);
+                    acc(j, c, f, ma[c], rcp_fast(var), vo.y);
+                    if (NF > BIGNF) P2[j][c] *= var; else P[j][c] *= var;
+                }
             }
         }
-    };
-    if constexpr (ROLL && DL_MONT_ROLL) {
-        constexpr int A4 = F0 & ~3, B4 = F0 + ((NG - F0) & ~3);
-#pragma unroll 1
-        for (int f = 0; f < A4; f += 4) pair2(f, P);
-        if (A4 < F0) pair(A4, P);
-#pragma unroll 1
-        for (int f = F0; f < B4; f += 4) pair2(f, P2);
-        if (B4 < NG) pair(B4, P2);
-    } else {
-#pragma unroll (ROLL ? BAND_UNROLL1 : NF)
-    for (int f = 0; f < F0; f += 2) pair(f, P);
-#pragma unroll (ROLL ? BAND_UNROLL1 : NF)
-    for (int f = F0; f < NG; f += 2) pair(f, P2);
-    }
-    if (NF - NG == 1) {
-        constexpr int f = NF - 1;
-        double ma[ZJ], ca[ZJ];
-#pragma unroll
-        for (int c = 0; c < ZJ; ++c) { ma[c] = md.m(c, f); ca[c] = md.cv(c, f); }
-#pragma unroll
-        for (int j = 0; j < TJ; ++j) {
-            const double2 vo = tc1[j][f];
-#pragma unroll
-            for (int c = 0; c < ZJ; ++c) {
-                const double var = fma(e2[j][c], ca[c], vo.x);
-                acc(j, c, f, ma[c], rcp_fast(var), vo.y);
-                if (NF > BIGNF) P2[j][c] *= var; else P[j][c] *= var;
-            }
-        }
-    }
     }
     // chi2 and (det)^-1/2 (utils_cy.pyx:111-118)
 #pragma unroll
