@@ -216,3 +216,25 @@ def test_c_abi_rejects_bad_arguments_before_any_device_work():
     assert L.dl_metrics_dev(ll(0), ll(10), P, ll(10), P, None, P, None) == 1
     assert L.dl_fused_workspace_bytes(ll(64), ll(1000), ll(300), 1) < \
         L.dl_fused_workspace_bytes(ll(64), ll(1000), ll(300), 0)
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """The drop-in boundary is a C ABI: include/delight_b200.h compiles as pedantic C99 (no C++ or
+    torch types in any signature) and a C program links against the library and calls it."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "delight_b200.h"\n'
+                   'int main(void) { return dl_version() > 0 && dl_fused_padded_nz(1500) == 1536 '
+                   '? 0 : 1; }\n')
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    libdir = os.path.dirname(delight_b200.__file__)
+    exe = str(tmp_path / "abi")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", inc,
+                        str(src), "-o", exe, "-L", libdir, "-ldelight_b200",
+                        "-Wl,-rpath," + libdir], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True)
+    assert r.returncode == 0, r.stdout
+    assert subprocess.run([exe]).returncode == 0
