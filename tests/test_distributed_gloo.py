@@ -56,3 +56,32 @@ def test_gather_rows_world2_gloo(tmp_path):
     for rank, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert "rank %d ok" % rank in o
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank0():
+    """bench.py --impl reference launched the way the driver launches the scaling run (torchrun,
+    2 ranks, no GPU needed): rank 0 alone runs the compiled reference on the host cores and prints
+    ONE JSON line; the other rank exits 0 without work.  Reduced workload (300 training galaxies,
+    16 targets) so that it takes seconds."""
+    import json
+    import pytest
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    env = dict(os.environ, PYTHONPATH=REPO + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+         "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+         os.path.join(REPO, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+         "--warmup", "0", "--train", "300", "--targets", "16"],
+        env=env, cwd=REPO, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["steps"] == 1
+    assert d["metric"] == "galaxy-PDFs/sec" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
