@@ -9,7 +9,6 @@ Everything numeric happens in libdelight_b200.so; torch is used for device memor
 index plumbing (gather/scatter of target rows) only.
 """
 import ctypes
-import os
 
 import numpy as np
 

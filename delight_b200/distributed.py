@@ -8,8 +8,6 @@ collective; `gather_rows` is the only communication and works on any torch.distr
 """
 import os
 
-import numpy as np
-
 from .apply import partition  # noqa: F401  (re-export)
 
 

@@ -5,8 +5,6 @@ contract as delight/utils_cy.pyx; the arithmetic runs in CUDA (libdelight_b200.s
 NumPy arrays (any strides); like the Cython typed-memoryview coercion, a wrong dtype or rank
 raises ValueError before anything is computed.
 """
-import ctypes
-
 import numpy as np
 
 from . import _lib
