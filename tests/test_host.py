@@ -238,3 +238,35 @@ def test_header_is_plain_c_and_links(tmp_path):
                        text=True)
     assert r.returncode == 0, r.stdout
     assert subprocess.run([exe]).returncode == 0
+
+
+def test_binary_catalogues_read_like_the_text_files(golden, tmp_path):
+    """a catalogue named *.npy in the cfg is the same table in binary.  The reader
+    must return exactly what it returns for the text file -- whole file and a rank's slice --
+    and the row counters / savers must agree on both formats."""
+    from delight_b200 import pipeline
+    g = golden("sdss_pipeline")
+    wd = str(tmp_path)
+    np.savetxt(wd + "/ta.txt", g["target_cat"], fmt="%.18e")
+    np.save(wd + "/ta.npy", np.loadtxt(wd + "/ta.txt", ndmin=2))
+    names = ["U_SDSS", "G_SDSS", "R_SDSS", "I_SDSS", "Z_SDSS"]
+    base = dict(bandNames=names, target_bandOrder=str(g["target_bandOrder"]).split(" "),
+                target_referenceBand="I_SDSS",
+                training_extraFracFluxError=float(g["extraFrac"]))   # (the reader's training-key quirk)
+    n = g["target_cat"].shape[0]
+    assert pipeline._count_rows(wd + "/ta.txt") == pipeline._count_rows(wd + "/ta.npy") == n
+    for first, last in ((None, None), (3, n - 2)):
+        got = {}
+        for ext in ("txt", "npy"):
+            p = dict(base, target_catFile=wd + "/ta." + ext)
+            got[ext] = pipeline.read_catalogue(p, "target_", first, last) \
+                if first is not None else pipeline.read_catalogue(p, "target_")
+        (a, na), (b, nb) = got["txt"], got["npy"]
+        assert na == nb and len(a) == len(b) > 0
+        for f in ("fluxes", "fluxes_var", "bands", "nf", "ztrue"):
+            np.testing.assert_array_equal(getattr(a, f), getattr(b, f))
+    arr = np.arange(12.).reshape(4, 3) / 7
+    pipeline._save(wd + "/o.npy", arr, "%.2e")
+    pipeline._save(wd + "/o.txt", arr, "%.2e")
+    np.testing.assert_array_equal(pipeline._load(wd + "/o.npy"), arr)               # lossless
+    np.testing.assert_allclose(pipeline._load(wd + "/o.txt"), arr, rtol=5e-3)       # %.2e text
